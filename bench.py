@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py - decoder queries/sec on the BASELINE workload (Panoptic CMU0 shapes, V=5,
+Q=1024, L=4, bf16 pyramid, B=1), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+* "step"  = one DQDecoder.forward (L layers, all V views) over one frame of synthetic input.
+* `value` = B*Q*steps / device time, inputs resident in HBM when the timed region starts.
+* `e2e`   = same metric through the public API with pinned HOST buffers: H2D of the step's
+            inputs and D2H of poses + scores inside the timed region.
+* N > 1   = the Q queries are sharded over N ranks (contiguous blocks, strong scaling), every
+            rank holds the pyramid, one NCCL all-gather of final poses per step
+            (mvgformer_b200/sharding.py).
+* `--impl reference` = the CPU oracle port of the reference decoder on the host cores
+            (the reference is Python and /root/reference does not exist on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "decoder queries/sec (Q=1024,V=5,L=4)"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--queries", type=int, default=1024)
+    ap.add_argument("--views", type=int, default=5)
+    ap.add_argument("--layers", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--threshold", type=float, default=0.1)
+    ap.add_argument("--gemm", default=None, choices=[None, "tcgen05", "cublas"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {
+        "workload": f"Panoptic CMU0 shapes, {a.views} views, Q={a.queries}, L={a.layers}, "
+                    f"bf16 pyramid, B={a.batch} frame(s) per step (BASELINE.json configs[1])",
+        "views": a.views, "queries": a.queries, "layers": a.layers, "batch": a.batch,
+        "joints": 15, "levels": [[128, 240], [64, 120], [32, 60]], "threshold": a.threshold,
+        "parallelism": "single GPU" if world == 1 else f"query-sharded x{world} + all-gather",
+        "l2": "per-step working set (103 MB pyramid + 0.7 GB value/offset maps) exceeds the "
+              "126 MB L2, no explicit flush",
+    }
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi while the timed region runs (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 8:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def cpu_reference_steps(a, steps, warmup, verbose=False):
+    """Times the oracle port of the reference decoder on the host cores.
+
+    Sample (bounded): ONE of the L decoder layers at the full Q/V/pyramid size; the layers
+    have identical cost, so decoder time = L x layer time.  The oracle batches the per-query
+    SVD loop and skips the reference's host-side cv2 work, i.e. it is faster than the
+    reference's own Python - a conservative baseline."""
+    import numpy as np
+    import torch
+    from mvgformer_b200 import synthetic as syn
+    from oracle import decoder_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sc = syn.make_scene(batch=a.batch, n_views=a.views, num_instance=a.queries, seed=0)
+    sd = syn.make_decoder_state_dict(a.layers, np.random.default_rng(1))
+    prm = orc.layer_params(sd, 0)
+
+    def one():
+        with torch.no_grad():
+            return orc.decoder_layer_forward(prm, sc["tgt"], sc["query_pos"], sc["reference_points"],
+                                             sc["src_views"], sc["spatial_shapes"],
+                                             sc["level_start_index"], sc["meta"], sc["img_size"],
+                                             threshold=a.threshold)
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    qps = a.batch * a.queries / (dt * a.layers)
+    sample = (f"oracle port, fp32, {cores} threads: 1 of {a.layers} decoder layers at full size "
+              f"(B={a.batch}, V={a.views}, Q={a.queries}), {steps} timed + {warmup} warm-up passes, "
+              f"{dt:.2f} s/layer, decoder time = {a.layers} x layer")
+    return qps, dt * a.layers * 1e3, cores, sample
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # keep the whole run within a few minutes: cap the number of CPU passes
+    steps, warmup = a.steps, a.warmup
+    t_probe = time.perf_counter()
+    qps, ms, cores, sample = cpu_reference_steps(a, 1, 0)
+    per = time.perf_counter() - t_probe
+    budget = 150.0
+    max_passes = max(1, int(budget / max(per, 1e-3)))
+    w_eff = min(warmup, max(0, max_passes // 4))
+    k_eff = max(1, min(steps, max_passes - w_eff))
+    qps, ms, cores, sample = cpu_reference_steps(a, k_eff, w_eff)
+    if k_eff != steps or w_eff != warmup:
+        sample += f" (requested {steps}+{warmup} passes capped to {k_eff}+{w_eff} to stay within minutes)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, 1),
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from types import SimpleNamespace as NS
+    import mvgformer_b200 as mvg
+    from mvgformer_b200 import _lib, linear as mlinear, profiling as prof, sharding
+    from mvgformer_b200 import synthetic as syn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if a.gemm:
+        mlinear.set_backend(a.gemm)
+    _lib.load()
+
+    B, V, Q, L, J = a.batch, a.views, a.queries, a.layers, 15
+    sc = syn.make_scene(batch=B, n_views=V, num_instance=Q, seed=0, feat_dtype=torch.bfloat16)
+    sd = syn.make_decoder_state_dict(L, np.random.default_rng(1))
+    cfg = NS(DECODER=NS(share_layer_weights=False),
+             MULTI_PERSON=NS(SPACE_SIZE=sc["space_size"], SPACE_CENTER=sc["space_center"]))
+    layer = mvg.DQDecoderLayer(sc["space_size"], sc["space_center"], sc["img_size"], 3, 256, 1024,
+                               0.1, "relu", 1, 8, 8, True, "cat_proj", V,
+                               "ablation_not_use_rayconv", "MLP", False, True, "threshold",
+                               visualization_jump_num=-1, bayesian_update=False,
+                               triangulation_method="linalg", filter_query=True, num_joints=J)
+    dec = mvg.DQDecoder(cfg, layer, L, True).eval()
+    dec.load_state_dict(sd, strict=False)
+    dec = dec.to(dev)
+
+    # host (pinned) copies for the e2e arm, device-resident copies for `value`
+    host = {k: sc[k].pin_memory() for k in ("tgt", "query_pos", "reference_points")}
+    host_feats = [s.pin_memory() for s in sc["src_views"]]
+    if world > 1:
+        for k in host:
+            host[k] = sharding.shard_points(host[k], Q, J, rank, world).pin_memory()
+    d = {k: v.to(dev) for k, v in host.items()}
+    feats = [s.to(dev) for s in host_feats]
+    meta = [{"camera": {k: v.to(dev) for k, v in m["camera"].items()}, "center": m["center"].to(dev),
+             "scale": m["scale"].to(dev), "inv_affine_trans": m["inv_affine_trans"].to(dev)}
+            for m in sc["meta"]]
+    shapes, lsi = sc["spatial_shapes"].to(dev), sc["level_start_index"].to(dev)
+    shard = (rank, world, None) if world > 1 else None
+    ql = (sharding.shard_bounds(Q, rank, world)[1] - sharding.shard_bounds(Q, rank, world)[0]) if world > 1 else Q
+
+    def forward(inp, fts):
+        with torch.no_grad():
+            hs, refs, refs2d, proj2d, cls = dec(inp["tgt"], inp["reference_points"], fts, meta, shapes,
+                                                lsi, None, query_pos=inp["query_pos"],
+                                                threshold=a.threshold, shard=shard)
+            poses, prob = refs[-1], cls[-1]
+            if world > 1:
+                poses = sharding.allgather_queries(poses, Q, J, world)
+                prob = sharding.allgather_queries(prob, Q, 1, world)
+        return poses, prob
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    # ---- device-resident throughput
+    for _ in range(max(a.warmup, 3)):
+        forward(d, feats)
+    clocks = ClockSampler(local)
+    clocks.start()
+    prof.reset()
+    prof.enable(True)
+    n0 = _lib.launch_count()
+    total_ms = timed(lambda: forward(d, feats), a.steps)
+    launches = (_lib.launch_count() - n0) // max(a.steps, 1)
+    prof.enable(False)
+    clk = clocks.stop()
+    stages = prof.summary()
+    value = B * Q * a.steps / (total_ms * 1e-3)
+
+    # ---- end to end: pinned host buffers in, poses + scores out, every step
+    e2e = None
+    if not a.no_e2e:
+        h2d = sum(t.numel() * t.element_size() for t in list(host.values()) + host_feats)
+        out_pose = torch.empty((B, Q * J, 3), dtype=torch.float32).pin_memory()
+        out_prob = torch.empty((B, Q, 2), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            fts = [s.to(dev, non_blocking=True) for s in host_feats]
+            poses, prob = forward(inp, fts)
+            out_pose.copy_(poses, non_blocking=True)
+            out_prob.copy_(prob, non_blocking=True)
+            torch.cuda.current_stream().synchronize()     # the caller consumes the result
+
+        for _ in range(3):
+            e2e_step()
+        e2e_ms = timed(e2e_step, a.steps)
+        e2e = {"value": B * Q * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(out_pose.numel() * 4 + out_prob.numel() * 4),
+               "ms_per_step": e2e_ms / a.steps}
+
+    # ---- roofline of the dominant kernel (fused projection + sampling), live CUDA events
+    n_pts = ql * J
+    S = int(sum(h * w for h, w in syn.PANOPTIC["levels"]))
+    alg_bytes = (V * B * S * 448 * 2          # value + offset/logit map of this layer, read once
+                 + B * n_pts * 192 * 4        # qproj
+                 + B * n_pts * 12             # 3D reference points
+                 + B * V * n_pts * 256 * 2    # sampled features out (bf16)
+                 + B * V * n_pts * (8 + 1)    # ref2d + bounding out
+                 + B * V * 256)               # packed cameras
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    st = stages.get("project_sample_fused", {"mean_ms": float("nan"), "count": 0})
+    achieved = alg_bytes / (st["mean_ms"] * 1e-3) / 1e9 if st["count"] else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("project_sample_fused_dram_bytes_per_launch")
+    roofline = {"kernel": "mvg::project_sample_kernel<3>", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": traffic, "algorithmic_bytes_per_launch": int(alg_bytes),
+                "launch_ms": st["mean_ms"], "launches_timed": st["count"], "peak_source": peak_src,
+                "stage_ms_per_step": {k: v["total_ms"] / a.steps for k, v in sorted(stages.items())}}
+
+    # ---- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        qps, _, cores, sample = cpu_reference_steps(a, 2, 1)
+        cpu = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": total_ms / a.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(a, world),
+            "gemm_backend": mlinear.get_backend(), "gpu_launches": int(launches),
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

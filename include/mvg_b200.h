@@ -1,0 +1,207 @@
+/*
+ * mvg_b200.h - C ABI of the B200-native (sm_100a) projective-attention decoder hot path.
+ *
+ * Drop-in boundary for XunshanMan/MVGFormer (reference citations are file:line relative to
+ * the reference root).  The reference binds its one native extension through pybind11
+ * (`Deformable.deform_forward/backward`, lib/models/ops/src/vision.cpp:24-27, declared in
+ * lib/models/ops/src/deform.h:31-72) and does everything else in Python.  This library
+ * exposes the same op plus the fused stages of `DQDecoderLayer.forward`
+ * (lib/models/dq_decoder.py:850-1045) as plain C functions:
+ *
+ *   - raw device pointers + explicit sizes, no torch types;
+ *   - the caller owns every buffer (PyTorch allocates), nothing is allocated or
+ *     synchronised inside, each call only enqueues kernels on `stream`
+ *     (a `cudaStream_t` passed as void*), re-entrant per stream - the same contract as the
+ *     reference wrapper, which launches on the current stream without sync
+ *     (lib/models/ops/src/cuda/deform_cuda.cu:76);
+ *   - return 0 on success, a negative MVG_E* code otherwise; `mvg_last_error()` returns a
+ *     thread-local message.  Unlike the reference (which only printf's launch errors,
+ *     deform_im2col_cuda.cuh:958-962) launch errors are returned.
+ *
+ * Shapes: B frames, V views, Q queries, J joints, N=Q*J points, C=256 channels, M=8 heads,
+ * D=32 channels/head, Lv pyramid levels (<= MVG_MAX_LEVELS), P=8 points, S=sum H_l*W_l.
+ * "bf16" pointers are `__nv_bfloat16` (uint16 storage).
+ */
+#ifndef MVG_B200_H_
+#define MVG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MVG_API __attribute__((visibility("default")))
+#else
+#define MVG_API
+#endif
+
+#define MVG_MAX_LEVELS 4
+#define MVG_MAX_VIEWS 8
+#define MVG_CAM_FLOATS 64 /* floats per packed camera record, see MvgCamera in csrc/common.cuh */
+
+enum {
+  MVG_OK = 0,
+  MVG_EINVAL = -1,  /* bad argument (null pointer, unsupported shape / dtype) */
+  MVG_ELAUNCH = -2, /* CUDA launch / runtime error (message holds cudaGetErrorString) */
+  MVG_EUNSUPPORTED = -3
+};
+
+enum { MVG_F32 = 0, MVG_BF16 = 1 };
+
+/* Message for the last non-zero return on this thread. */
+MVG_API const char* mvg_last_error(void);
+/* ABI version of this header (bumped on any signature change). */
+MVG_API int mvg_abi_version(void);
+/* Number of kernels launched by this library in this process (for bench accounting). */
+MVG_API int64_t mvg_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Deformable.deform_forward  (lib/models/ops/src/deform.h:31-50,
+ * lib/models/ops/src/cuda/deform_cuda.cu:31-91, kernel deform_im2col_cuda.cuh:247-309)
+ *   value (B,S,M,D) dtype `dtype`; spatial_shapes (Lv,2) int64 DEVICE; level_start_index
+ *   (Lv) int64 DEVICE; sampling_loc (B,Lq,M,Lv,P,2) and attn_weight (B,Lq,M,Lv,P) dtype
+ *   `dtype`; out (B,Lq,M*D) dtype `dtype`, fully overwritten (the reference zero-fills it,
+ *   deform_cuda.cu:65).  fp32 accumulation.  D must be 32, M*D <= 1024.
+ *   `im2col_step` is accepted for signature fidelity; batch % min(batch, step) == 0 is
+ *   enforced like deform_cuda.cu:63, the chunk loop itself is not needed.
+ */
+MVG_API int mvg_deform_forward(const void* value, const int64_t* spatial_shapes,
+                       const int64_t* level_start_index, const void* sampling_loc,
+                       const void* attn_weight, int dtype, int batch, int spatial_size,
+                       int num_heads, int channels, int num_levels, int num_query,
+                       int num_point, int im2col_step, void* out, void* stream);
+
+/* Deformable.deform_backward (deform.h:52-72, deform_cuda.cu:94-164, col2im kernels
+ * deform_im2col_cuda.cuh:311-930).  fp32 only.  grad_value (B,S,M,D) must be ZEROED by the
+ * caller (the reference allocates it with at::zeros, deform_cuda.cu:129); grad_sampling_loc
+ * and grad_attn_weight are fully overwritten. */
+MVG_API int mvg_deform_backward(const float* value, const int64_t* spatial_shapes,
+                        const int64_t* level_start_index, const float* sampling_loc,
+                        const float* attn_weight, const float* grad_output, int batch,
+                        int spatial_size, int num_heads, int channels, int num_levels,
+                        int num_query, int num_point, int im2col_step, float* grad_value,
+                        float* grad_sampling_loc, float* grad_attn_weight, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Pyramid hand-off: NCHW maps -> one channels-last bf16 matrix (rows, S, C).
+ * Replaces `input_flatten = cat([src.flatten(2)...]).permute(0,2,1)`
+ * (lib/models/ops/modules/projattn.py:160).  src_l: (rows, C, H_l*W_l) fp32 or bf16;
+ * dst: (rows, S, C) bf16; level l occupies positions [start_l, start_l + H_l*W_l).
+ */
+MVG_API int mvg_pyramid_to_channels_last(const void* const* src_levels, int src_dtype, int num_levels,
+                                 const int* level_hw /* Lv: H_l*W_l */, int rows, int channels,
+                                 void* dst_bf16, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense projection on tcgen05 tensor cores:  out = act(A @ W^T + bias)
+ *   A (M,K) bf16 row-major, lda = K;  W (Nout,K) bf16 row-major (nn.Linear layout);
+ *   bias (Nout) fp32 or NULL; out (M,Nout) bf16 or fp32 (`out_dtype`), row stride ldo
+ *   elements.  relu != 0 applies max(0, .).  K % 64 == 0, Nout % 16 == 0.
+ * Used for: value/rayconv + the per-level sampling_offsets/attention_weights projections of
+ * the raw pyramid (projattn.py:169,180-181), output_proj (:203), feature_update_mlp, FFN,
+ * offset_net MLP (dq_decoder.py:101,284,289-292).
+ */
+MVG_API int mvg_linear_bf16(const void* A, const void* W, const float* bias, void* out, int out_dtype,
+                    int64_t M, int Nout, int K, int64_t ldo, int relu, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused projection + projective attention sampling for all (b, v, n):
+ *   a3  project_ref_points   (dq_decoder.py:331-397, cameras.py:167-207, transforms.py:135-141)
+ *   a4  ProjAttn minus the dense GEMMs (projattn.py:139-153 ref-point feature lookup,
+ *       :180-191 offsets / softmax over Lv*P / sampling locations incl. the layout scramble)
+ *   a5  multi-scale deformable gather (deform_im2col_cuda.cuh:247-309)
+ * Inputs:
+ *   ref3d (B,N,3) fp32 world mm;  cams (B,V,MVG_CAM_FLOATS) fp32 packed cameras;
+ *   vg (V*B, S, ld_vg) bf16, row r = v*B + b: columns [0,256) = value (rayconv output),
+ *       [256,384) = sampling_offsets.weight @ feat, [384,448) = attention_weights.weight @ feat
+ *       (both WITHOUT bias; bilinear interpolation commutes with the linear map);
+ *   qproj (B,N,192) fp32 = [sampling_offsets; attention_weights](tgt + query_pos) + bias.
+ * Outputs:
+ *   sampled (B,V,N,256) bf16 (input of output_proj), ref2d (B,V,N,2) fp32 normalised
+ *   network-image coordinates, bounding (B,V,N) uint8.
+ * ProjAttn.forward entry (projattn.py:115): when `refl_in` (B,V,N,Lv,2) is non-NULL the
+ *   projection is skipped and the per-level normalised reference points are read from it
+ *   (ref3d, cams, ref2d, bounding may then be NULL).
+ */
+typedef struct {
+  int batch, views, points;     /* B, V, N */
+  int num_levels;               /* Lv (3 for the shipped configs) */
+  int level_h[MVG_MAX_LEVELS];
+  int level_w[MVG_MAX_LEVELS];
+  int level_start[MVG_MAX_LEVELS];
+  int spatial_size;             /* S */
+  int ld_vg;                    /* row stride of vg in elements (>= 448) */
+  float img_w, img_h;           /* network image size (NETWORK.IMAGE_SIZE) */
+} MvgSampleParams;
+
+MVG_API int mvg_project_sample_fused(const float* ref3d, const float* cams, const void* vg,
+                             const float* qproj, const MvgSampleParams* prm, void* sampled,
+                             float* ref2d, uint8_t* bounding, const float* refl_in,
+                             void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Integer path of the query filter (dq_decoder.py:596-656): threshold mask, torch.where
+ * order, per-frame counts, padding to the max count with query id 0, stable sort by frame,
+ * and the reverse (un-pad) ids.  prob (B,Q,2) fp32.  method 0 = 'threshold'
+ * (prob[...,1] > thr), 1 = 'all' (prob[...,0] > 0).
+ * min_one != 0 applies the "always one query" rule (:620-623) locally; query-sharded ranks
+ * pass 0 and apply it after a global count (mvgformer_b200/sharding.py).
+ * Outputs (device): selected (B,Q) uint8 incl. the "always one query" rule (:620-623);
+ * counts (B) int32; info (4) int32 = {n_valid, max_count, 0, 0}; batch_ids / query_ids
+ * (capacity B*Q, first B*max_count valid) int64; batch_ids_rev / query_ids_rev
+ * (capacity B*Q, first n_valid valid) int64.  The id arrays may be NULL.
+ */
+MVG_API int mvg_select_pad(const float* prob, int batch, int queries, float threshold, int method,
+                   int min_one, uint8_t* selected, int32_t* counts, int32_t* info, int64_t* batch_ids,
+                   int64_t* query_ids, int64_t* batch_ids_rev, int64_t* query_ids_rev,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Offsets -> refined 2D -> DLT triangulation, with the scatter/zero-fill semantics of
+ * dq_decoder.py:1011-1029:
+ *   a9  calculate_2d_offsets tail (:678-707): offset/img_size, refined = proj + offset,
+ *       x img_size, confidence softmax over views
+ *   a10 inverse affine, 5-iteration undistort (:119-204), P = K[R|-RT] (:223-246)
+ *   a11 DLT (lib/mvn/utils/multiview.py:170-228): smallest right singular vector of the
+ *       confidence-weighted 2Vx4 system, solved as a 4x4 symmetric eigenproblem of A^T A by
+ *       cyclic Jacobi in fp64 (more accurate than the reference's fp32 LAPACK SVD).
+ * mlp_out (B*V*N rows, row stride mlp_ld >= 3 floats) fp32 = offset_net output
+ * (dx, dy, conf-logit) in columns 0..2; ref2d (B,V,N,2);
+ * selected (B,Q) uint8.  Outputs: new_ref (B,N,3), refined_abs (B,V,N,2), projs_abs
+ * (B,V,N,2) fp32 - zeros where the query is not selected.
+ */
+MVG_API int mvg_offsets_dlt(const float* mlp_out, int mlp_ld, const float* ref2d,
+                    const uint8_t* selected, const float* cams, int batch, int views,
+                    int queries, int joints, float img_w, float img_h, float* new_ref,
+                    float* refined_abs, float* projs_abs, void* stream);
+
+/* multiview.triangulate_batch_of_points_batch_version (lib/mvn/utils/multiview.py:257-269):
+ * proj (n,V,3,4) fp32, points (n,V,J,2) fp32, conf (n,V,J) fp32 or NULL -> out (n,J,3). */
+MVG_API int mvg_triangulate(const float* proj, const float* points, const float* conf, int n,
+                    int views, int joints, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused elementwise stages of update_feature (dq_decoder.py:763-778, :845-848):
+ *   mvg_masked_view_mean: aver[b,n,:] = mean_v( bounding[b,v,n] * x[b,v,n,:] )   (bf16 io)
+ *   mvg_add_layernorm   : out = LayerNorm(a + b) * gamma + beta  (rows x 256; a fp32, b bf16
+ *                         or fp32; writes fp32 and optionally a bf16 copy for the next GEMM)
+ *   mvg_class_prob      : prob[b,q,:] = mean_j sigmoid(cls[b,q*J+j,:])  (dq_decoder.py:889-893)
+ */
+MVG_API int mvg_masked_view_mean(const void* x_bf16, const uint8_t* bounding, int batch, int views,
+                         int points, int channels, void* out_bf16, void* stream);
+MVG_API int mvg_add_layernorm(const float* a, const void* b, int b_dtype, const float* gamma,
+                      const float* beta, int64_t rows, int channels, float eps, float* out_f32,
+                      void* out_bf16, void* stream);
+MVG_API int mvg_class_prob(const float* cls, int batch, int queries, int joints, float* prob,
+                   void* stream);
+/* class_embed Linear(256,2) + sigmoid + mean over joints in one pass (fp32):
+ * x (B, Q*J, 256) fp32, w (2,256), bias (2) -> prob (B,Q,2). */
+MVG_API int mvg_class_head(const float* x, const float* w, const float* bias, int batch, int queries,
+                   int joints, float* prob, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVG_B200_H_ */

@@ -1,0 +1,16 @@
+"""mvgformer_b200 - B200-native (sm_100a) projective-attention decoder for MVGFormer.
+
+Host-side mirror of the reference's operator / module interface for ONE hot path
+(SURVEY.md section 8): `Deformable.deform_forward/backward`, `DeformFunction`, `ProjAttn`,
+`DQDecoderLayer`, `DQDecoder`, `multiview.triangulate_batch_of_points_batch_version`.
+All arithmetic runs in hand-written CUDA behind the C ABI of include/mvg_b200.h.
+"""
+from . import _lib  # noqa: F401
+from .deformable import deform_forward, deform_backward, install_as_Deformable  # noqa: F401
+from .deform_func import DeformFunction  # noqa: F401
+from .projattn import ProjAttn  # noqa: F401
+from .dq_decoder import DQDecoder, DQDecoderLayer, MLP, offset_net  # noqa: F401
+from . import multiview  # noqa: F401
+
+__all__ = ["deform_forward", "deform_backward", "install_as_Deformable", "DeformFunction",
+           "ProjAttn", "DQDecoder", "DQDecoderLayer", "MLP", "offset_net", "multiview"]

@@ -1,0 +1,20 @@
+// Error plumbing + version for libmvg_b200.
+#include "common.cuh"
+
+namespace mvg {
+
+static thread_local char t_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace mvg
+
+extern "C" const char* mvg_last_error(void) { return mvg::t_err; }
+extern "C" int mvg_abi_version(void) { return 1; }
+extern "C" int64_t mvg_launch_count(void) { return mvg::g_launches.load(); }

@@ -1,0 +1,312 @@
+// Fused projection + projective-attention sampling: one warp per (frame b, view v, point n).
+//
+//   a3  project_ref_points      lib/models/dq_decoder.py:331-397, lib/utils/cameras.py:167-207,
+//                               lib/utils/transforms.py:135-141
+//   a4  ProjAttn (non-GEMM part) lib/models/ops/modules/projattn.py:139-153 (ref-point feature
+//                               lookup), :180-191 (offsets, softmax over Lv*P, locations, and the
+//                               `.view` layout scramble of the per-level Linear outputs)
+//   a5  deformable gather       lib/models/ops/src/cuda/deform_im2col_cuda.cuh:247-309, :41-93
+//
+// Restructuring vs the reference:
+//   * The per-level Linear on (grid_sample(feat_l) + query) is split by linearity into
+//     bilinear-sampling a pre-projected 192-channel map G = feat @ [W_off; W_attn]^T (written by
+//     the same tcgen05 GEMM that produces `value`) plus a per-point term qproj = W (tgt+pos) + b.
+//     The 59 MB + 118 MB attention-weight / sampling-location tensors of the reference never
+//     exist; they live in a few KB of shared memory per warp.
+//   * Phase B computes, once per (head, sample), the four bilinear*attention weights and the
+//     base texel offset and stages them in shared memory; phase C is then a branch-free stream of
+//     LDG.128 (lane = head*4 + chunk, 8 bf16 channels per lane) + fp32 FMAs.
+// Geometry and the sampling index path use non-contracted fp32 ops in the reference's op order.
+#include "common.cuh"
+
+namespace mvg {
+
+constexpr int kWarps = 4;          // warps per CTA
+constexpr int kItemsPerWarp = 8;   // consecutive work items per warp per CTA iteration
+constexpr int kQP = 192;           // 128 offset channels + 64 logit channels per level
+constexpr int kHeads = 8;
+constexpr int kVgValueCols = 256;  // value columns precede the G columns in a vg row
+constexpr int kMaxNS = MVG_MAX_LEVELS * 8;
+
+struct WarpScratch {
+  float proj[MVG_MAX_LEVELS][kQP];        // per pyramid level: Linear outputs (offsets | logits)
+  float4 cw[kHeads * (kMaxNS + 1)];       // per (head, sample): 4 corner weights * attention
+  int base[kHeads * (kMaxNS + 1)];        // per (head, sample): texel offset | dx flag | dy flag
+};
+
+template <int LV>
+__global__ void __launch_bounds__(kWarps * 32, 4)
+project_sample_kernel(const float* __restrict__ ref3d, const MvgCamera* __restrict__ cams,
+                      const __nv_bfloat16* __restrict__ vg, const float* __restrict__ qproj,
+                      const MvgSampleParams prm, __nv_bfloat16* __restrict__ sampled,
+                      float* __restrict__ ref2d_out, uint8_t* __restrict__ bounding_out,
+                      const float* __restrict__ refl_in) {
+  __shared__ WarpScratch scratch[kWarps];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  WarpScratch& sc = scratch[warp];
+  const int N = prm.points, V = prm.views, B = prm.batch;
+  const int64_t total = static_cast<int64_t>(B) * V * N;
+  const int ld = prm.ld_vg;
+  constexpr int NS = LV * 8;           // samples per head
+  constexpr int NSP = NS + 1;          // padded stride (bank-conflict-free across heads)
+  constexpr int kChunk = kWarps * kItemsPerWarp;
+  const int m = lane >> 2, sub = lane & 3;
+
+  for (int64_t base_item = static_cast<int64_t>(blockIdx.x) * kChunk; base_item < total;
+       base_item += static_cast<int64_t>(gridDim.x) * kChunk) {
+#pragma unroll 1
+    for (int it = 0; it < kItemsPerWarp; ++it) {
+      const int64_t item = base_item + warp + it * kWarps;
+      if (item >= total) break;
+      const int n = static_cast<int>(item % N);
+      const int bv = static_cast<int>(item / N);
+      const int v = bv % V, b = bv / V;
+      const int64_t out_idx = (static_cast<int64_t>(b) * V + v) * N + n;
+      const __nv_bfloat16* vrow = vg + static_cast<int64_t>(v * B + b) * prm.spatial_size * ld;
+      float refl_x[LV], refl_y[LV];
+      if (refl_in != nullptr) {          // ProjAttn.forward entry: reference points are given
+#pragma unroll
+        for (int l = 0; l < LV; ++l) {
+          refl_x[l] = __ldg(refl_in + (out_idx * LV + l) * 2);
+          refl_y[l] = __ldg(refl_in + (out_idx * LV + l) * 2 + 1);
+        }
+      } else {
+        // ---------------- a3: projection (all lanes redundantly; same addresses -> broadcast)
+        const MvgCamera* cam = cams + bv;   // (B,V) row-major == item / N
+        const float* x3 = ref3d + (static_cast<int64_t>(b) * N + n) * 3;
+        const float dx = fsub(__ldg(x3 + 0), cam->T[0]);
+        const float dy = fsub(__ldg(x3 + 1), cam->T[1]);
+        const float dz = fsub(__ldg(x3 + 2), cam->T[2]);
+        const float xc = fadd(fadd(fmul(cam->R[0], dx), fmul(cam->R[1], dy)), fmul(cam->R[2], dz));
+        const float yc = fadd(fadd(fmul(cam->R[3], dx), fmul(cam->R[4], dy)), fmul(cam->R[5], dz));
+        const float zc = fadd(fadd(fmul(cam->R[6], dx), fmul(cam->R[7], dy)), fmul(cam->R[8], dz));
+        const float zden = fadd(zc, 1e-5f);
+        float y0 = fdiv(xc, zden), y1 = fdiv(yc, zden);
+        const float r2 = fadd(fmul(y0, y0), fmul(y1, y1));
+        const float r4 = fmul(r2, r2), r6 = fmul(fmul(r2, r2), r2);
+        const float radial = fadd(1.f, fadd(fadd(fmul(cam->k[0], r2), fmul(cam->k[1], r4)),
+                                            fmul(cam->k[2], r6)));
+        const float tanv = fadd(fmul(cam->p[0], y1), fmul(cam->p[1], y0));
+        const float corr = fadd(radial, fmul(2.f, tanv));
+        y0 = fadd(fmul(y0, corr), fmul(cam->p[1], r2));
+        y1 = fadd(fmul(y1, corr), fmul(cam->p[0], r2));
+        float px = fadd(fmul(cam->f[0], y0), cam->c[0]);
+        float py = fadd(fmul(cam->f[1], y1), cam->c[1]);
+        const bool inb = (px >= 0.f) && (py >= 0.f) && (px < cam->wh[0]) && (py < cam->wh[1]);
+        px = fminf(fmaxf(px, -1.f), cam->clamp_max);
+        py = fminf(fmaxf(py, -1.f), cam->clamp_max);
+        const float ax = fadd(fadd(fmul(px, cam->aff[0]), fmul(py, cam->aff[1])), cam->aff[2]);
+        const float ay = fadd(fadd(fmul(px, cam->aff[3]), fmul(py, cam->aff[4])), cam->aff[5]);
+        const float rx = fdiv(ax, prm.img_w), ry = fdiv(ay, prm.img_h);
+        if (lane == 0) {
+          ref2d_out[2 * out_idx] = rx;
+          ref2d_out[2 * out_idx + 1] = ry;
+          bounding_out[out_idx] = inb ? 1 : 0;
+        }
+#pragma unroll
+        for (int l = 0; l < LV; ++l) {   // dq_decoder.py:570-573
+          const float fW = static_cast<float>(prm.level_w[l]), fH = static_cast<float>(prm.level_h[l]);
+          refl_x[l] = fdiv(fmul(rx, fW), fsub(fW, 1.f));
+          refl_y[l] = fdiv(fmul(ry, fH), fsub(fH, 1.f));
+        }
+      }
+
+      // ---------------- phase A (a4 i+iii): sample the pre-projected map G at the reference point
+      if (lane < kQP / 8) {
+        const float* qp = qproj + (static_cast<int64_t>(b) * N + n) * kQP + lane * 8;
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(qp));
+        const float4 q1 = __ldg(reinterpret_cast<const float4*>(qp + 4));
+        const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        uint4 cn[LV][4];
+        float cwgt[LV][4];
+#pragma unroll
+        for (int l = 0; l < LV; ++l) {
+          const int W = prm.level_w[l], H = prm.level_h[l];
+          // F.grid_sample(bilinear, zeros, align_corners=False): projattn.py:139-153
+          const float gx = fminf(fmaxf(fsub(fmul(refl_x[l], 2.f), 1.f), -1.1f), 1.1f);
+          const float gy = fminf(fmaxf(fsub(fmul(refl_y[l], 2.f), 1.f), -1.1f), 1.1f);
+          const float ix = fsub(fmul(fadd(gx, 1.f), fmul(static_cast<float>(W), 0.5f)), 0.5f);
+          const float iy = fsub(fmul(fadd(gy, 1.f), fmul(static_cast<float>(H), 0.5f)), 0.5f);
+          const float fx0 = floorf(ix), fy0 = floorf(iy);
+          const int x0 = static_cast<int>(fx0), yy0 = static_cast<int>(fy0);
+          const float we = fsub(ix, fx0), ww = fsub(1.f, we);
+          const float ws = fsub(iy, fy0), wn = fsub(1.f, ws);
+          const bool okx0 = x0 >= 0 && x0 < W, okx1 = x0 + 1 >= 0 && x0 + 1 < W;
+          const bool oky0 = yy0 >= 0 && yy0 < H, oky1 = yy0 + 1 >= 0 && yy0 + 1 < H;
+          const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
+          const int ya = min(max(yy0, 0), H - 1), yb = min(max(yy0 + 1, 0), H - 1);
+          const __nv_bfloat16* gl = vrow + static_cast<int64_t>(prm.level_start[l]) * ld +
+                                    kVgValueCols + lane * 8;
+          cn[l][0] = ldg_nc_v4(gl + static_cast<int64_t>(ya * W + xa) * ld);
+          cn[l][1] = ldg_nc_v4(gl + static_cast<int64_t>(ya * W + xb) * ld);
+          cn[l][2] = ldg_nc_v4(gl + static_cast<int64_t>(yb * W + xa) * ld);
+          cn[l][3] = ldg_nc_v4(gl + static_cast<int64_t>(yb * W + xb) * ld);
+          cwgt[l][0] = (oky0 && okx0) ? wn * ww : 0.f;
+          cwgt[l][1] = (oky0 && okx1) ? wn * we : 0.f;
+          cwgt[l][2] = (oky1 && okx0) ? ws * ww : 0.f;
+          cwgt[l][3] = (oky1 && okx1) ? ws * we : 0.f;
+        }
+#pragma unroll
+        for (int l = 0; l < LV; ++l) {
+          float acc[8], t[8];
+          unpack8(cn[l][0], t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = cwgt[l][0] * t[i];
+#pragma unroll
+          for (int c = 1; c < 4; ++c) {
+            unpack8(cn[l][c], t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += cwgt[l][c] * t[i];
+          }
+          float4* dst = reinterpret_cast<float4*>(&sc.proj[l][lane * 8]);
+          dst[0] = make_float4(acc[0] + qv[0], acc[1] + qv[1], acc[2] + qv[2], acc[3] + qv[3]);
+          dst[1] = make_float4(acc[4] + qv[4], acc[5] + qv[5], acc[6] + qv[6], acc[7] + qv[7]);
+        }
+      }
+      __syncwarp();
+
+      // ---------------- phase B (a4 iv+v, a5 index path): per (head, sample) parameters.
+      // 4 lanes per head, lane `sub` owns samples r = sub + 4 i.
+      {
+        float lg[NS / 4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NS / 4; ++i) {
+          const int g = m * NS + sub + 4 * i;          // flat logit index after the `.view`
+          lg[i] = sc.proj[g >> 6][128 + (g & 63)];
+          mx = fmaxf(mx, lg[i]);
+        }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NS / 4; ++i) {
+          lg[i] = expf(lg[i] - mx);
+          sum += lg[i];
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+#pragma unroll
+        for (int i = 0; i < NS / 4; ++i) {
+          const int r = sub + 4 * i;
+          const int l = i >> 1;                        // == r >> 3 because sub < 4 (static index)
+          const float wgt = lg[i] / sum;
+          const int f = m * (NS * 2) + 2 * r;          // flat offset index after the `.view`
+          const float2 off = *reinterpret_cast<const float2*>(&sc.proj[f >> 7][f & 127]);
+          const int W = prm.level_w[l], H = prm.level_h[l], start = prm.level_start[l];
+          const float rlx = refl_x[l], rly = refl_y[l];
+          const float fW = static_cast<float>(W), fH = static_cast<float>(H);
+          // projattn.py:186-191, then deform_im2col_cuda.cuh:291-301 and :41-93
+          const float loc_x = fadd(rlx, fdiv(off.x, fW));
+          const float loc_y = fadd(rly, fdiv(off.y, fH));
+          const float h_im = fsub(fmul(loc_y, fH), 0.5f);
+          const float w_im = fsub(fmul(loc_x, fW), 0.5f);
+          const bool inside = h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW;
+          const float fh = floorf(h_im), fw = floorf(w_im);
+          const int h_low = inside ? static_cast<int>(fh) : 0;
+          const int w_low = inside ? static_cast<int>(fw) : 0;
+          const float lh = h_im - fh, lw = w_im - fw;
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          const bool okh0 = inside && h_low >= 0, okh1 = inside && h_low + 1 <= H - 1;
+          const bool okw0 = inside && w_low >= 0, okw1 = inside && w_low + 1 <= W - 1;
+          const int ha = max(h_low, 0), wa = max(w_low, 0);
+          const int hb = min(h_low + 1, H - 1), wb = min(w_low + 1, W - 1);
+          float4 cwv;
+          cwv.x = (okh0 && okw0) ? hh * hw * wgt : 0.f;
+          cwv.y = (okh0 && okw1) ? hh * lw * wgt : 0.f;
+          cwv.z = (okh1 && okw0) ? lh * hw * wgt : 0.f;
+          cwv.w = (okh1 && okw1) ? lh * lw * wgt : 0.f;
+          // texel index of the (ha, wa) corner; bit0: +1 texel for the right column exists,
+          // bit1: +W texels for the lower row exists (otherwise the clamped corner aliases).
+          const int tex = start + ha * W + wa;
+          sc.cw[m * NSP + r] = cwv;
+          sc.base[m * NSP + r] = (tex << 2) | ((wb > wa) ? 1 : 0) | ((hb > ha) ? 2 : 0);
+        }
+      }
+      __syncwarp();
+
+      // ---------------- phase C (a5): gather 4 corners x NS samples, 8 channels per lane
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      const __nv_bfloat16* vlane = vrow + m * 32 + sub * 8;
+#pragma unroll
+      for (int l = 0; l < LV; ++l) {
+        const int64_t rowstep = static_cast<int64_t>(prm.level_w[l]) * ld;
+#pragma unroll 4
+        for (int p = 0; p < 8; ++p) {
+          const int r = l * 8 + p;
+          const float4 cwv = sc.cw[m * NSP + r];
+          const int bs = sc.base[m * NSP + r];
+          const __nv_bfloat16* p00 = vlane + static_cast<int64_t>(bs >> 2) * ld;
+          const int64_t dxo = (bs & 1) ? ld : 0;
+          const int64_t dyo = (bs & 2) ? rowstep : 0;
+          const uint4 c1 = ldg_nc_v4(p00);
+          const uint4 c2 = ldg_nc_v4(p00 + dxo);
+          const uint4 c3 = ldg_nc_v4(p00 + dyo);
+          const uint4 c4 = ldg_nc_v4(p00 + dyo + dxo);
+          float t[8];
+          unpack8(c1, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += cwv.x * t[i];
+          unpack8(c2, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += cwv.y * t[i];
+          unpack8(c3, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += cwv.z * t[i];
+          unpack8(c4, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += cwv.w * t[i];
+        }
+      }
+      uint4 o;
+      o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(sampled + out_idx * 256 + lane * 8) = o;
+      __syncwarp();   // scratch is reused by the next item
+    }
+  }
+}
+
+}  // namespace mvg
+
+extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, const void* vg,
+                                        const float* qproj, const MvgSampleParams* prm,
+                                        void* sampled, float* ref2d, uint8_t* bounding,
+                                        const float* refl_in, void* stream) {
+  using namespace mvg;
+  MVG_REQUIRE(vg && qproj && prm && sampled, "mvg_project_sample_fused: null pointer");
+  MVG_REQUIRE(refl_in || (ref3d && cams && ref2d && bounding),
+              "mvg_project_sample_fused: projection inputs/outputs missing");
+  MVG_REQUIRE(prm->num_levels >= 1 && prm->num_levels <= MVG_MAX_LEVELS,
+              "mvg_project_sample_fused: num_levels %d out of range", prm->num_levels);
+  MVG_REQUIRE(prm->batch > 0 && prm->views > 0 && prm->points > 0, "mvg_project_sample_fused: empty shape");
+  MVG_REQUIRE(prm->ld_vg >= 448 && prm->ld_vg % 8 == 0, "mvg_project_sample_fused: ld_vg %d", prm->ld_vg);
+  int s = 0;
+  for (int l = 0; l < prm->num_levels; ++l) {
+    MVG_REQUIRE(prm->level_h[l] > 1 && prm->level_w[l] > 1 && prm->level_start[l] == s,
+                "mvg_project_sample_fused: level %d shape/start inconsistent", l);
+    s += prm->level_h[l] * prm->level_w[l];
+  }
+  MVG_REQUIRE(s == prm->spatial_size, "mvg_project_sample_fused: spatial_size %d != sum H*W %d",
+              prm->spatial_size, s);
+  MVG_REQUIRE(static_cast<int64_t>(s) * prm->ld_vg < (1ll << 29),
+              "mvg_project_sample_fused: per-view map too large for 32-bit texel offsets");
+  const int64_t total = static_cast<int64_t>(prm->batch) * prm->views * prm->points;
+  const int64_t chunks = (total + kWarps * kItemsPerWarp - 1) / (kWarps * kItemsPerWarp);
+  const int64_t max_grid = static_cast<int64_t>(kNumSMs) * 16;
+  const int grid = static_cast<int>(chunks < max_grid ? chunks : max_grid);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const MvgCamera* cam = reinterpret_cast<const MvgCamera*>(cams);
+  const __nv_bfloat16* vgp = static_cast<const __nv_bfloat16*>(vg);
+  __nv_bfloat16* sp = static_cast<__nv_bfloat16*>(sampled);
+  switch (prm->num_levels) {
+    case 1: project_sample_kernel<1><<<grid, kWarps * 32, 0, st>>>(ref3d, cam, vgp, qproj, *prm, sp, ref2d, bounding, refl_in); break;
+    case 2: project_sample_kernel<2><<<grid, kWarps * 32, 0, st>>>(ref3d, cam, vgp, qproj, *prm, sp, ref2d, bounding, refl_in); break;
+    case 3: project_sample_kernel<3><<<grid, kWarps * 32, 0, st>>>(ref3d, cam, vgp, qproj, *prm, sp, ref2d, bounding, refl_in); break;
+    default: project_sample_kernel<4><<<grid, kWarps * 32, 0, st>>>(ref3d, cam, vgp, qproj, *prm, sp, ref2d, bounding, refl_in); break;
+  }
+  return check_launch("mvg_project_sample_fused");
+}

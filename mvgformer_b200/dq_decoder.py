@@ -1,0 +1,327 @@
+"""`DQDecoderLayer` / `DQDecoder` mirrors (lib/models/dq_decoder.py:248-1172,
+lib/models/mvp_decoder.py:49-104,266-341) on the B200 kernels.
+
+Same constructor arguments, forward signatures, return tuples and state_dict keys as the
+reference, so `load_state_dict` of a reference checkpoint binds
+(`layers.{i}.proj_attn.*`, `feature_update_mlp`, `norm1/2/3`, `linear1/2`, `self_attn.*`,
+`pose_embed.MLP.layers.*`, `class_embed`).  Only the shipped configuration
+(configs/panoptic/knn5-lr4-q1024.yaml:106-166) is built: feature_update_method='MLP',
+init_self_attention=False, open_forward_ffn=True, bayesian_update=False,
+triangulation_method in {'linalg','batch'}; anything else raises NotImplementedError.
+
+One layer = the following device work (no host synchronisation anywhere):
+  1. vg     = pyramid @ [rayconv; sampling_offsets; attention_weights]^T   tensor cores
+     (hoisted into DQDecoder.forward: one GEMM for all L layers, the pyramid is read once)
+  2. qproj  = (tgt + query_pos) @ [sampling_offsets; attention_weights]^T + b
+  3. mvg_project_sample_fused: projection + offsets/softmax + deformable gather (a3-a5)
+  4. output_proj GEMM, bounding mask, view mean, feature_update_mlp, LayerNorm, FFN, LayerNorm
+  5. mvg_class_head + mvg_select_pad (integer path, a8)
+  6. offset_net MLP (3 GEMMs) per view
+  7. mvg_offsets_dlt: offsets, view-softmax confidences, inverse affine, undistort, DLT,
+     zero-fill scatter (a9-a11)
+`match_ref_points_to_gt` (dq_decoder.py:1055-1096, "visualization only", result unused for
+triangulation_method='linalg') is not reproduced.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from . import profiling as prof
+from .cameras import pack_cameras
+from .linear import linear
+from .projattn import ProjAttn
+
+
+class MLP(nn.Module):
+    """lib/models/multi_view_pose_transformer.py:81-102 (parameter container; the
+    arithmetic runs through `linear`)."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        h = [hidden_dim] * (num_layers - 1)
+        self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
+
+
+class offset_net(nn.Module):
+    """lib/models/dq_decoder.py:97-111."""
+
+    def __init__(self, in_dim, hid_dim, layer_num):
+        super().__init__()
+        self.MLP = MLP(in_dim, hid_dim, 3, layer_num)
+
+
+def _get_clones(module, N):
+    return nn.ModuleList([copy.deepcopy(module) for _ in range(N)])
+
+
+class DecoderContext:
+    """Per-call device state shared by all layers: channels-last pyramid, packed cameras,
+    the pre-projected value/offset/logit map `vg` and static shape info."""
+
+    def __init__(self, src_views: Sequence[torch.Tensor], meta: List[Dict], img_size,
+                 layers: Sequence["DQDecoderLayer"], batch_size: int):
+        dev = src_views[0].device
+        self.levels = [(int(s.shape[2]), int(s.shape[3])) for s in src_views]
+        self.batch = batch_size
+        self.views = src_views[0].shape[0] // batch_size
+        self.img_size = [float(img_size[0]), float(img_size[1])]
+        self.cams = pack_cameras(meta, img_size, device=dev)                 # (B,V,64)
+        with prof.stage("pyramid_to_cl"):
+            feat_cl = ops.pyramid_to_channels_last(src_views)                # (V*B,S,256) bf16
+        # one GEMM for all distinct layers: the pyramid is read from HBM once
+        distinct: List[DQDecoderLayer] = []
+        for l in layers:
+            if all(l is not d for d in distinct):
+                distinct.append(l)
+        packs = [l.proj_attn.packed_weights() for l in distinct]
+        if len(distinct) == 1:
+            w_all, b_all = packs[0]["w_vg"], packs[0]["b_vg"]
+        else:
+            key = tuple(id(p["w_vg"]) for p in packs)
+            cached = getattr(layers[0], "_vg_cat_cache", None)
+            if cached is None or cached[0] != key:
+                cached = (key, torch.cat([p["w_vg"] for p in packs], 0).contiguous(),
+                          torch.cat([p["b_vg"] for p in packs], 0).contiguous())
+                layers[0]._vg_cat_cache = cached
+            w_all, b_all = cached[1], cached[2]
+        with prof.stage("vg_gemm"):
+            self.vg_all = linear(feat_cl, w_all, b_all)                      # (V*B,S,448*Ld)
+        self.ld_vg = self.vg_all.shape[-1]
+        self._slot = {id(l): i for i, l in enumerate(distinct)}
+
+    def vg_for(self, layer: "DQDecoderLayer") -> torch.Tensor:
+        i = self._slot[id(layer)]
+        return self.vg_all[..., i * 448:]
+
+
+class DQDecoderLayer(nn.Module):
+    def __init__(self, space_size, space_center, img_size, pose_embed_layer, d_model=256,
+                 d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4,
+                 detach_refpoints_cameraprj=True, fuse_view_feats='mean', n_views=5,
+                 projattn_posembed_mode='use_rayconv', feature_update_method='MLP',
+                 init_self_attention=False, open_forward_ffn=False,
+                 query_filter_method='threshold', visualization_jump_num=200,
+                 bayesian_update=False, triangulation_method='linalg', filter_query=True,
+                 num_joints=15):
+        super().__init__()
+        # parameters in the reference's registration order / names (dq_decoder.py:273-315)
+        self.proj_attn = ProjAttn(d_model, n_levels, n_heads, n_points, projattn_posembed_mode)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.self_attn = nn.MultiheadAttention(d_model, n_heads, dropout=dropout)
+        self.feature_update_mlp = nn.Linear(d_model, d_model)
+        self.dropout2 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        if activation != "relu":
+            raise NotImplementedError(f"activation={activation!r}: only 'relu' is built for B200")
+        self.activation = F.relu
+        self.dropout3 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout4 = nn.Dropout(dropout)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.grid_size = torch.tensor(space_size)
+        self.grid_center = torch.tensor(space_center)
+        self.img_size = img_size
+        self.detach_refpoints_cameraprj = detach_refpoints_cameraprj
+        self.fuse_view_feats = fuse_view_feats
+        self.pose_embed = offset_net(d_model, d_model, pose_embed_layer)
+        self.softmax_conf = nn.Softmax(dim=0)
+        self.open_bayesian_update = bayesian_update
+        if bayesian_update:
+            raise NotImplementedError("bayesian_update=True is not built for B200")
+        self.use_confidences = False
+        self.class_embed = nn.Linear(d_model, 2)
+        self.num_joints = num_joints
+        self.feature_update_method = feature_update_method
+        self.init_self_attention = init_self_attention
+        self.open_forward_ffn = open_forward_ffn
+        self.query_filter_method = query_filter_method
+        self.visualization_jump_num = visualization_jump_num
+        self.triangulation_method = triangulation_method
+        self.filter_query = filter_query
+        self.d_model, self.d_ffn, self.pose_embed_layer = d_model, d_ffn, pose_embed_layer
+        self._wcache = None
+        if feature_update_method != 'MLP':
+            raise NotImplementedError(f"feature_update_method={feature_update_method!r}: only 'MLP'")
+        if init_self_attention:
+            raise NotImplementedError("init_self_attention=True is not built for B200")
+        if not open_forward_ffn:
+            raise NotImplementedError("open_forward_ffn=False is not built for B200")
+        if triangulation_method not in ('linalg', 'batch'):
+            raise NotImplementedError(f"triangulation_method={triangulation_method!r}: only "
+                                      "'linalg' / 'batch' (same DLT) are built for B200")
+        if query_filter_method != 'threshold':
+            raise NotImplementedError(f"query_filter_method={query_filter_method!r}: only 'threshold'")
+        if d_model != 256 or d_ffn % 64 != 0:
+            raise NotImplementedError("B200 kernels are specialised for d_model=256")
+
+    @staticmethod
+    def with_pos_embed(tensor, pos):
+        return tensor if pos is None else tensor + pos
+
+    def norm2absolute(self, norm_coords):        # mvp_decoder.py:100-105
+        device = norm_coords.device
+        gs, gc = self.grid_size.to(device), self.grid_center.to(device)
+        return norm_coords * gs + gc - gs / 2.0
+
+    # ------------------------------------------------------------------ weight packing
+    def packed_weights(self):
+        mods = [self.feature_update_mlp, self.linear1, self.linear2, self.class_embed,
+                self.norm2, self.norm3] + list(self.pose_embed.MLP.layers)
+        ps = [p for m in mods for p in (m.weight, m.bias)]
+        key = tuple((p.data_ptr(), p._version, p.device) for p in ps)
+        if self._wcache is not None and self._wcache[0] == key:
+            return self._wcache[1]
+        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().float().contiguous()
+        with torch.no_grad():
+            pk = dict(w_fu=bf(self.feature_update_mlp.weight), b_fu=f32(self.feature_update_mlp.bias),
+                      w1=bf(self.linear1.weight), b1=f32(self.linear1.bias),
+                      w2=bf(self.linear2.weight), b2=f32(self.linear2.bias),
+                      wc=f32(self.class_embed.weight), bc=f32(self.class_embed.bias),
+                      g2=f32(self.norm2.weight), e2=f32(self.norm2.bias),
+                      g3=f32(self.norm3.weight), e3=f32(self.norm3.bias), mlp=[])
+            nl = len(self.pose_embed.MLP.layers)
+            for i, lyr in enumerate(self.pose_embed.MLP.layers):
+                w, b = lyr.weight.detach(), lyr.bias.detach()
+                if i == nl - 1:                      # pad the 3-row head to a 16-row MMA tile
+                    wp = torch.zeros(16, w.shape[1], dtype=w.dtype, device=w.device)
+                    bp = torch.zeros(16, dtype=b.dtype, device=b.device)
+                    wp[:3], bp[:3] = w, b
+                    w, b = wp, bp
+                pk["mlp"].append((bf(w), f32(b)))
+        self._wcache = (key, pk)
+        return pk
+
+    # ------------------------------------------------------------------ the layer
+    def _forward_ctx(self, tgt, query_pos, reference_points, ctx: DecoderContext, *,
+                     threshold, indices=None, return_debug=False, shard=None):
+        B, N, C = tgt.shape
+        J = self.num_joints
+        Q = N // J
+        V = ctx.views
+        pw = self.proj_attn.packed_weights()
+        lw = self.packed_weights()
+        ref3d = reference_points.detach().reshape(B, N, 3).float().contiguous()
+        tgt = tgt.float().contiguous()
+        # 2. per-point part of the offset / logit projections
+        with prof.stage("qproj"):
+            q_bf = (tgt if query_pos is None else tgt + query_pos).to(torch.bfloat16)
+            qproj = linear(q_bf, pw["w_q"], pw["b_q"], out_dtype=torch.float32)  # (B,N,192)
+        # 3. fused projection + sampling
+        vg = ctx.vg_for(self)
+        prm = ops.make_sample_params(B, V, N, ctx.levels, ctx.ld_vg, ctx.img_size)
+        with prof.stage("project_sample_fused"):
+            sampled, ref2d, bounding = ops.project_sample_fused(ref3d, ctx.cams, vg, qproj, prm)
+        # 4. output_proj, mask, view-mean, update MLP, LN, FFN, LN
+        with prof.stage("output_proj"):
+            attn = linear(sampled, pw["w_o"], pw["b_o"])                          # (B,V,N,256) bf16
+            attn = attn * bounding.unsqueeze(-1).to(attn.dtype)                   # :585-586
+        with prof.stage("update_feature"):
+            aver = ops.masked_view_mean(attn, bounding)                           # :770
+            t2 = linear(aver, lw["w_fu"], lw["b_fu"])
+            tu, tu_bf = ops.add_layernorm(tgt, t2, lw["g2"], lw["e2"], self.norm2.eps)
+            hdn = linear(tu_bf, lw["w1"], lw["b1"], relu=True)
+            ff = linear(hdn, lw["w2"], lw["b2"])
+            tgt_update, _ = ops.add_layernorm(tu, ff, lw["g3"], lw["e3"], self.norm3.eps, want_bf16=False)
+        # 5. class head + query filter (integer path)
+        with prof.stage("class_head"):
+            prob = ops.class_head(tgt_update, lw["wc"], lw["bc"], Q, J)           # (B,Q,2)
+        if self.filter_query and indices is not None:
+            selected = torch.zeros((B, Q), dtype=torch.uint8, device=tgt.device)
+            for b, qs in enumerate(indices):
+                if len(qs):
+                    selected[b, torch.as_tensor(qs, device=tgt.device, dtype=torch.long)] = 1
+            selected[0, 0] |= (selected.sum() == 0).to(torch.uint8)              # :620-623
+        else:
+            method = "threshold" if self.filter_query else "all"
+            selected, _, info = ops.select_pad(prob, threshold, method, min_one=shard is None)
+            if shard is not None:                    # (rank, world, group): global :620-623 rule
+                from .sharding import apply_global_min_one
+                selected = apply_global_min_one(selected, info, shard[0], shard[2])
+        # 6. offset_net MLP per view
+        with prof.stage("offset_mlp"):
+            h = attn
+            nl = len(lw["mlp"])
+            for i, (w, b) in enumerate(lw["mlp"]):
+                last = i == nl - 1
+                h = linear(h, w, b, relu=not last, out_dtype=torch.float32 if last else torch.bfloat16)
+            mlp_out = h.view(B * V * N, -1)
+        # 7. offsets -> undistort -> DLT -> scatter
+        with prof.stage("offsets_dlt"):
+            new_ref, refined_abs, projs_abs = ops.offsets_dlt(mlp_out, ref2d, selected, ctx.cams,
+                                                              Q, J, ctx.img_size)
+        out = (tgt_update, new_ref, refined_abs, projs_abs, prob)
+        if return_debug:
+            return out, dict(sampled=sampled, ref2d=ref2d, bounding=bounding, attn=attn,
+                             selected=selected, mlp_out=mlp_out, qproj=qproj)
+        return out
+
+    def forward(self, tgt, query_pos, reference_points, src_views, src_spatial_shapes,
+                level_start_index, meta, src_padding_mask=None, rgb_views=None,
+                output_dir='./', frame_id=None, indices=None, threshold=0.5, indices_all=None):
+        """Signature and 5-tuple of dq_decoder.py:850-853,1045."""
+        ctx = DecoderContext(src_views, meta, self.img_size, [self], tgt.shape[0])
+        return self._forward_ctx(tgt, query_pos, reference_points, ctx, threshold=threshold,
+                                 indices=indices)
+
+
+class DQDecoder(nn.Module):
+    def __init__(self, cfg, decoder_layer, num_layers, return_intermediate=False):
+        super().__init__()
+        if cfg.DECODER.share_layer_weights:          # mvp_decoder.py:272-275
+            self.layers = nn.ModuleList([decoder_layer for _ in range(num_layers)])
+        else:
+            self.layers = _get_clones(decoder_layer, num_layers)
+        self.num_layers = num_layers
+        self.return_intermediate = return_intermediate
+        self.pose_embed = None
+        self.class_embed = None
+        self.grid_size = torch.tensor(cfg.MULTI_PERSON.SPACE_SIZE)
+        self.grid_center = torch.tensor(cfg.MULTI_PERSON.SPACE_CENTER)
+
+    def absolute2norm(self, absolute_coords):        # mvp_decoder.py:283-290
+        device = absolute_coords.device
+        gs, gc = self.grid_size.to(device), self.grid_center.to(device)
+        return (absolute_coords - gc + gs / 2.0) / gs
+
+    def norm2absolute(self, norm_coords):            # mvp_decoder.py:292-297
+        device = norm_coords.device
+        gs, gc = self.grid_size.to(device), self.grid_center.to(device)
+        return norm_coords * gs + gc - gs / 2.0
+
+    def forward(self, tgt, reference_points, src_views, meta, src_spatial_shapes,
+                src_level_start_index, src_valid_ratios, query_pos=None, src_padding_mask=None,
+                rgb_views=None, output_dir='./', frame_id=None, indices=None, threshold=0.5,
+                indices_all=None, shard=None):
+        """dq_decoder.py:1107-1172.  Extension: `shard=(rank, world, group)` runs this rank's
+        contiguous query block (tgt / reference_points / query_pos already sliced with
+        sharding.shard_points); the caller all-gathers the returned poses."""
+        if not tgt.is_cuda:
+            raise RuntimeError("Not implemented on the CPU")
+        ctx = DecoderContext(src_views, meta, self.layers[0].img_size, list(self.layers), tgt.shape[0])
+        output = tgt
+        inter, inter_ref, inter_2d, inter_proj, classes = [], [], [], [], []
+        ref_points_2d = None
+        for layer in self.layers:
+            output, reference_points, ref_points_2d, projs_2d_absolute, outputs_class = \
+                layer._forward_ctx(output, query_pos, reference_points, ctx, threshold=threshold,
+                                   indices=indices, shard=shard)
+            if self.return_intermediate:
+                inter.append(output)
+                inter_ref.append(reference_points)
+                inter_2d.append(ref_points_2d)
+                inter_proj.append(projs_2d_absolute)
+                classes.append(outputs_class)
+        if self.return_intermediate:
+            return torch.stack(inter), torch.stack(inter_ref), torch.stack(inter_2d), \
+                torch.stack(inter_proj), classes
+        return output, reference_points, ref_points_2d

@@ -1,0 +1,176 @@
+"""Thin Python launchers for the fused kernels of libmvg_b200 (one function per C entry point).
+
+Each function allocates outputs with torch, passes raw device pointers + the current CUDA
+stream to the C ABI and returns torch tensors.  No arithmetic happens here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MvgSampleParams, check, dtype_code, stream_ptr
+
+
+def pyramid_to_channels_last(src_views: Sequence[torch.Tensor]) -> torch.Tensor:
+    """list of Lv (rows, C, H_l, W_l) fp32/bf16 -> (rows, S, C) bf16 (projattn.py:160)."""
+    lib = _lib.load()
+    _lib.require_cuda(*src_views)
+    rows, ch = src_views[0].shape[0], src_views[0].shape[1]
+    dt = src_views[0].dtype
+    srcs = [s if s.is_contiguous() else s.contiguous() for s in src_views]
+    hw = [s.shape[2] * s.shape[3] for s in srcs]
+    dst = torch.empty((rows, sum(hw), ch), dtype=torch.bfloat16, device=srcs[0].device)
+    ptrs = (C.c_void_p * len(srcs))(*[s.data_ptr() for s in srcs])
+    hws = (C.c_int * len(srcs))(*hw)
+    check(lib.mvg_pyramid_to_channels_last(ptrs, dtype_code(dt), len(srcs), hws, rows, ch,
+                                           dst.data_ptr(), stream_ptr(dst.device)),
+          "mvg_pyramid_to_channels_last")
+    return dst
+
+
+def linear_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *,
+                relu: bool = False, out_dtype=torch.bfloat16,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act(a @ w^T + bias) on tcgen05.  a (..., K) bf16 contiguous, w (Nout, K) bf16."""
+    lib = _lib.load()
+    K = a.shape[-1]
+    M = a.numel() // K
+    nout = w.shape[0]
+    if out is None:
+        out = torch.empty(a.shape[:-1] + (nout,), dtype=out_dtype, device=a.device)
+    check(lib.mvg_linear_bf16(a.data_ptr(), w.data_ptr(), _lib.ptr(bias), out.data_ptr(),
+                              dtype_code(out.dtype), M, nout, K, out.stride(-2) if out.dim() > 1 else nout,
+                              1 if relu else 0, stream_ptr(a.device)), "mvg_linear_bf16")
+    return out
+
+
+def make_sample_params(batch: int, views: int, points: int, levels: Sequence[Tuple[int, int]],
+                       ld_vg: int, img_size: Sequence[float]) -> MvgSampleParams:
+    prm = MvgSampleParams()
+    prm.batch, prm.views, prm.points = batch, views, points
+    prm.num_levels = len(levels)
+    start = 0
+    for i, (h, w) in enumerate(levels):
+        prm.level_h[i], prm.level_w[i], prm.level_start[i] = int(h), int(w), start
+        start += int(h) * int(w)
+    prm.spatial_size = start
+    prm.ld_vg = int(ld_vg)
+    prm.img_w, prm.img_h = float(img_size[0]), float(img_size[1])
+    return prm
+
+
+def project_sample_fused(ref3d: Optional[torch.Tensor], cams: Optional[torch.Tensor],
+                         vg: torch.Tensor, qproj: torch.Tensor, prm: MvgSampleParams,
+                         refl: Optional[torch.Tensor] = None):
+    """-> sampled (B,V,N,256) bf16, ref2d (B,V,N,2) fp32, bounding (B,V,N) uint8."""
+    lib = _lib.load()
+    dev = vg.device
+    B, V, N = prm.batch, prm.views, prm.points
+    sampled = torch.empty((B, V, N, 256), dtype=torch.bfloat16, device=dev)
+    ref2d = torch.empty((B, V, N, 2), dtype=torch.float32, device=dev)
+    bounding = torch.empty((B, V, N), dtype=torch.uint8, device=dev)
+    check(lib.mvg_project_sample_fused(_lib.ptr(ref3d), _lib.ptr(cams), vg.data_ptr(),
+                                       qproj.data_ptr(), C.byref(prm), sampled.data_ptr(),
+                                       ref2d.data_ptr(), bounding.data_ptr(), _lib.ptr(refl),
+                                       stream_ptr(dev)), "mvg_project_sample_fused")
+    return sampled, ref2d, bounding
+
+
+def select_pad(prob: torch.Tensor, threshold: float, method: str = "threshold",
+               with_ids: bool = False, min_one: bool = True):
+    """Integer path of dq_decoder.py:596-656.  -> selected (B,Q) uint8, counts (B) i32,
+    info (4) i32 [n_valid, max_count]; optionally the four int64 id arrays (capacity B*Q)."""
+    lib = _lib.load()
+    B, Q, _ = prob.shape
+    dev = prob.device
+    selected = torch.empty((B, Q), dtype=torch.uint8, device=dev)
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    info = torch.empty((4,), dtype=torch.int32, device=dev)
+    ids: List[Optional[torch.Tensor]] = [None] * 4
+    if with_ids:
+        ids = [torch.zeros((B * Q,), dtype=torch.int64, device=dev) for _ in range(4)]
+    code = {"threshold": 0, "all": 1}[method]
+    check(lib.mvg_select_pad(prob.data_ptr(), B, Q, float(threshold), code, 1 if min_one else 0,
+                             selected.data_ptr(),
+                             counts.data_ptr(), info.data_ptr(), _lib.ptr(ids[0]),
+                             _lib.ptr(ids[1]), _lib.ptr(ids[2]), _lib.ptr(ids[3]),
+                             stream_ptr(dev)), "mvg_select_pad")
+    if with_ids:
+        return selected, counts, info, ids
+    return selected, counts, info
+
+
+def offsets_dlt(mlp_out: torch.Tensor, ref2d: torch.Tensor, selected: torch.Tensor,
+                cams: torch.Tensor, queries: int, joints: int, img_size: Sequence[float]):
+    """-> new_ref (B,N,3), refined_abs (B,V,N,2), projs_abs (B,V,N,2) fp32."""
+    lib = _lib.load()
+    B, V, N, _ = ref2d.shape
+    dev = ref2d.device
+    new_ref = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+    refined = torch.empty((B, V, N, 2), dtype=torch.float32, device=dev)
+    projs = torch.empty((B, V, N, 2), dtype=torch.float32, device=dev)
+    check(lib.mvg_offsets_dlt(mlp_out.data_ptr(), int(mlp_out.stride(-2)), ref2d.data_ptr(), selected.data_ptr(),
+                              cams.data_ptr(), B, V, queries, joints, float(img_size[0]),
+                              float(img_size[1]), new_ref.data_ptr(), refined.data_ptr(),
+                              projs.data_ptr(), stream_ptr(dev)), "mvg_offsets_dlt")
+    return new_ref, refined, projs
+
+
+def triangulate(proj: torch.Tensor, points: torch.Tensor,
+                conf: Optional[torch.Tensor]) -> torch.Tensor:
+    """proj (n,V,3,4), points (n,V,J,2), conf (n,V,J)|None -> (n,J,3), all fp32 CUDA."""
+    lib = _lib.load()
+    n, V, J, _ = points.shape
+    out = torch.empty((n, J, 3), dtype=torch.float32, device=points.device)
+    if n == 0:
+        return out
+    check(lib.mvg_triangulate(proj.data_ptr(), points.data_ptr(), _lib.ptr(conf), n, V, J,
+                              out.data_ptr(), stream_ptr(points.device)), "mvg_triangulate")
+    return out
+
+
+def masked_view_mean(x: torch.Tensor, bounding: torch.Tensor) -> torch.Tensor:
+    """x (B,V,N,C) bf16, bounding (B,V,N) uint8 -> (B,N,C) bf16."""
+    lib = _lib.load()
+    B, V, N, Cc = x.shape
+    out = torch.empty((B, N, Cc), dtype=torch.bfloat16, device=x.device)
+    check(lib.mvg_masked_view_mean(x.data_ptr(), bounding.data_ptr(), B, V, N, Cc,
+                                   out.data_ptr(), stream_ptr(x.device)), "mvg_masked_view_mean")
+    return out
+
+
+def add_layernorm(a: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                  eps: float = 1e-5, want_bf16: bool = True):
+    """LayerNorm(a + b): a fp32 (...,256), b bf16|fp32 -> (fp32, bf16|None)."""
+    lib = _lib.load()
+    rows = a.numel() // a.shape[-1]
+    out = torch.empty_like(a)
+    out_bf = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device) if want_bf16 else None
+    check(lib.mvg_add_layernorm(a.data_ptr(), b.data_ptr(), dtype_code(b.dtype), gamma.data_ptr(),
+                                beta.data_ptr(), rows, a.shape[-1], float(eps), out.data_ptr(),
+                                _lib.ptr(out_bf), stream_ptr(a.device)), "mvg_add_layernorm")
+    return out, out_bf
+
+
+def class_prob(cls: torch.Tensor, queries: int, joints: int) -> torch.Tensor:
+    """cls (B, Q*J, 2) fp32 -> (B,Q,2) = mean_j sigmoid (dq_decoder.py:889-893)."""
+    lib = _lib.load()
+    B = cls.shape[0]
+    prob = torch.empty((B, queries, 2), dtype=torch.float32, device=cls.device)
+    check(lib.mvg_class_prob(cls.data_ptr(), B, queries, joints, prob.data_ptr(),
+                             stream_ptr(cls.device)), "mvg_class_prob")
+    return prob
+
+
+def class_head(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, queries: int,
+               joints: int) -> torch.Tensor:
+    """class_embed + sigmoid + mean over joints: x (B,Q*J,256) fp32 -> prob (B,Q,2)."""
+    lib = _lib.load()
+    B = x.shape[0]
+    prob = torch.empty((B, queries, 2), dtype=torch.float32, device=x.device)
+    check(lib.mvg_class_head(x.data_ptr(), w.data_ptr(), bias.data_ptr(), B, queries, joints,
+                             prob.data_ptr(), stream_ptr(x.device)), "mvg_class_head")
+    return prob

@@ -1,0 +1,194 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on
+seeded synthetic inputs.  Run in the build container only:
+
+    python -m oracle.gen_golden
+
+Inputs are NOT stored: they are regenerated from `numpy.random.default_rng(seed)` by
+mvgformer_b200.synthetic (bit-stable across platforms); each fixture stores an input
+checksum so that a drifted generator is detected instead of silently compared.
+
+Fixtures (all produced by reference code, file:line given per entry):
+  decoder_small.npz   DQDecoderLayer.forward run layer by layer with teacher forcing
+                      (lib/models/dq_decoder.py:850-1045) + DQDecoder.forward (:1107-1172)
+  projattn_small.npz  ProjAttn.forward (lib/models/ops/modules/projattn.py:115-204)
+  deform_core.npz     deform_core_pytorch (lib/models/ops/functions/deform_func.py:68-99)
+  project_ref.npz     DQDecoderLayer.project_ref_points (dq_decoder.py:331-397) +
+                      get_affine_transform (lib/utils/transforms.py:72-112), Panoptic + Shelf
+  triangulate.npz     multiview.triangulate_batch_of_points_batch_version
+                      (lib/mvn/utils/multiview.py:257-269), fp32 (as shipped) and the same
+                      reference code fed float64 inputs (its exact-arithmetic answer)
+  state_dict_keys.json  parameter names/shapes of the reference DQDecoder
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from mvgformer_b200 import synthetic as syn  # noqa: E402
+from oracle.reference_harness import (build_reference_decoder, load_reference,  # noqa: E402
+                                      run_reference_decoder)
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+SMALL = dict(batch=2, n_views=3, num_instance=12, levels=((20, 36), (10, 18), (5, 9)),
+             seed=7, weight_seed=11, num_layers=2, threshold=0.1)
+
+
+def checksum(*tensors) -> str:
+    h = hashlib.sha256()
+    for t in tensors:
+        a = t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def scene_checksum(sc, sd) -> str:
+    ts = list(sc["src_views"]) + [sc["tgt"], sc["query_pos"], sc["reference_points"]]
+    for m in sc["meta"]:
+        ts += [m["camera"][k] for k in sorted(m["camera"])] + [m["center"], m["scale"], m["inv_affine_trans"]]
+    ts += [sd[k] for k in sorted(sd)]
+    return checksum(*ts)
+
+
+def small_scene():
+    sc = syn.make_scene(batch=SMALL["batch"], n_views=SMALL["n_views"],
+                        num_instance=SMALL["num_instance"], seed=SMALL["seed"],
+                        levels=SMALL["levels"])
+    sd = syn.make_decoder_state_dict(SMALL["num_layers"], np.random.default_rng(SMALL["weight_seed"]))
+    return sc, sd
+
+
+def gen_decoder():
+    sc, sd = small_scene()
+    dec = build_reference_decoder(sc, sd, SMALL["num_layers"])
+    out = {"input_checksum": scene_checksum(sc, sd)}
+    hs, refs, refs2d, proj2d, cls = run_reference_decoder(dec, sc, SMALL["threshold"])
+    # (hs of the full run equals the chained single-layer outputs bit for bit; not stored twice)
+    out.update(full_refs=refs.numpy(), full_refs2d=refs2d.numpy(),
+               full_proj2d=proj2d.numpy(), full_cls=torch.stack(cls).numpy())
+    hs_full = hs
+    # teacher-forced single layers: inputs of layer l are the reference's outputs of layer l-1
+    masks = [torch.zeros(f.shape[0], f.shape[2] * f.shape[3], dtype=torch.bool) for f in sc["src_views"]]
+    tgt, ref = sc["tgt"], sc["reference_points"]
+    with torch.no_grad():
+        for l in range(SMALL["num_layers"]):
+            o = dec.layers[l](tgt, sc["query_pos"], ref[:, :, None], sc["src_views"],
+                              sc["spatial_shapes"], sc["level_start_index"], sc["meta"], masks,
+                              threshold=SMALL["threshold"])
+            # layer-l inputs: l = 0 -> regenerated from the seed; l > 0 -> l{l-1}_out_tgt / _ref
+            assert torch.equal(o[0], hs_full[l])
+            for name, t in zip(("tgt", "ref", "refined2d", "proj2d", "prob"), o):
+                out[f"l{l}_out_{name}"] = t.numpy()
+            tgt, ref = o[0], o[1]
+    np.savez_compressed(os.path.join(GOLD, "decoder_small.npz"), **out)
+    keys = {k: list(v.shape) for k, v in dec.state_dict().items()}
+    with open(os.path.join(GOLD, "state_dict_keys.json"), "w") as f:
+        json.dump(keys, f, indent=1, sort_keys=True)
+
+
+def gen_projattn():
+    ns = load_reference()
+    sc, sd = small_scene()
+    rng = np.random.default_rng(21)
+    B = SMALL["batch"]
+    mod = ns.ProjAttn(256, 1, 8, 8, "ablation_not_use_rayconv").eval()
+    mod.load_state_dict({k[len("layers.0.proj_attn."):]: v for k, v in sd.items()
+                         if k.startswith("layers.0.proj_attn.")})
+    N = 64
+    query = torch.from_numpy(rng.standard_normal((B, N, 256), dtype=np.float32))
+    ref = torch.from_numpy(rng.uniform(-0.1, 1.1, size=(B, N, 3, 2)).astype(np.float32))
+    feats = [s[:B] for s in sc["src_views"]]
+    with torch.no_grad():
+        out = mod(query, ref, feats, None, sc["spatial_shapes"], sc["level_start_index"], None)
+    np.savez_compressed(os.path.join(GOLD, "projattn_small.npz"), out=out.numpy(),
+                        input_checksum=checksum(query, ref, *feats))
+
+
+def gen_deform_core():
+    ns = load_reference()
+    rng = np.random.default_rng(3)
+    shapes = [(9, 14), (5, 7), (3, 4)]
+    S = sum(h * w for h, w in shapes)
+    B, Lq, M, D, Lv, P = 2, 37, 8, 32, 3, 8
+    value = torch.from_numpy(rng.standard_normal((B, S, M, D), dtype=np.float32))
+    loc = torch.from_numpy(rng.uniform(-0.2, 1.2, size=(B, Lq, M, Lv, P, 2)).astype(np.float32))
+    attn = torch.softmax(torch.from_numpy(rng.standard_normal((B, Lq, M, Lv * P), dtype=np.float32)), -1) \
+        .view(B, Lq, M, Lv, P)
+    out = ns.deform_core_pytorch(value, shapes, loc, attn)
+    np.savez_compressed(os.path.join(GOLD, "deform_core.npz"), out=out.numpy(),
+                        input_checksum=checksum(value, loc, attn))
+
+
+def gen_project_ref():
+    ns = load_reference()
+    out = {}
+    for name, cfg in (("panoptic", syn.PANOPTIC), ("shelf", syn.SHELF)):
+        sc = syn.make_scene(cfg, batch=2, n_views=3, num_instance=40, seed=5,
+                            levels=((8, 8), (4, 4), (2, 2)))
+        sd = syn.make_decoder_state_dict(1, np.random.default_rng(1))
+        dec = build_reference_decoder(sc, sd, 1)
+        layer = dec.layers[0]
+        # spread the points so that some fall outside the images (bounding False + clamp)
+        ref = sc["reference_points"] * torch.tensor([1.6, 1.6, 1.0])
+        N = ref.shape[1]
+        for v in range(3):
+            r, b = layer.project_ref_points(ref[:, :, None], sc["meta"][v], 1, 2, N, "cpu")
+            out[f"{name}_ref2d_v{v}"] = r.reshape(2, N, 2).numpy()
+            out[f"{name}_bounding_v{v}"] = b.reshape(2, N).numpy()
+        m = sc["meta"][0]
+        out[f"{name}_affine"] = ns.transforms.get_affine_transform(m["center"][0], m["scale"][0], 0, sc["img_size"])
+        out[f"{name}_affine_inv"] = ns.transforms.get_affine_transform(m["center"][0], m["scale"][0], 0, sc["img_size"], inv=1)
+        out[f"{name}_ref_checksum"] = checksum(ref)
+    np.savez_compressed(os.path.join(GOLD, "project_ref.npz"), **out)
+
+
+def gen_triangulate():
+    ns = load_reference()
+    rng = np.random.default_rng(9)
+    cams = syn.make_ring_cameras(5, rng)
+    meta = syn.make_meta(cams, 1, (1920, 1080), (960, 512))
+    from oracle import decoder_oracle as orc
+    P = orc.proj_matrices([m["camera"] for m in meta])[0]                       # (V,3,4) fp32
+    n, J, V = 24, 15, 5
+    X = torch.from_numpy(rng.uniform([-2500, -3000, 0], [2500, 2000, 1800], size=(n, J, 3)))
+    Xh = torch.cat([X, torch.ones(n, J, 1, dtype=torch.float64)], -1)            # (n,J,4)
+    proj = torch.einsum("vrc,njc->nvjr", P.double(), Xh)
+    pts = (proj[..., :2] / proj[..., 2:3]).float()                              # exact projections
+    noisy = pts + torch.from_numpy(rng.standard_normal(pts.shape).astype(np.float32)) * 2.0
+    conf = torch.softmax(torch.from_numpy(rng.standard_normal((n, V, J)).astype(np.float32)), 1)
+    Pn = P.unsqueeze(0).expand(n, -1, -1, -1).contiguous()
+    f = ns.multiview.triangulate_batch_of_points_batch_version
+    out = dict(
+        exact_in_X=X.numpy(),
+        clean_fp32=f(Pn, pts, conf, solver="linalg").numpy(),
+        noisy_fp32=f(Pn, noisy, conf, solver="linalg").numpy(),
+        noisy_fp32_noconf=f(Pn, noisy, None, solver="linalg").numpy(),
+        # the same reference code fed float64 tensors: its exact-arithmetic answer
+        clean_fp64=f(Pn.double(), pts.double(), conf.double(), solver="linalg").numpy(),
+        noisy_fp64=f(Pn.double(), noisy.double(), conf.double(), solver="linalg").numpy(),
+        input_checksum=checksum(Pn, pts, noisy, conf))
+    np.savez_compressed(os.path.join(GOLD, "triangulate.npz"), **out)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(1)            # deterministic reduction order in the CPU kernels
+    gen_decoder()
+    gen_projattn()
+    gen_deform_core()
+    gen_project_ref()
+    gen_triangulate()
+    for fn in sorted(os.listdir(GOLD)):
+        print(fn, os.path.getsize(os.path.join(GOLD, fn)))
+
+
+if __name__ == "__main__":
+    main()

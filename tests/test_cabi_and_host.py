@@ -1,0 +1,97 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol declared in
+include/mvg_b200.h; host logic (camera packing, weight packing, error behaviour)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import mvgformer_b200 as mvg
+from mvgformer_b200 import _lib, cameras, synthetic as syn
+from helpers import small_scene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mvg_b200.h")).read()
+    return sorted(set(re.findall(r"MVG_API\s+[\w\s\*]+?\b(mvg_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = declared_symbols()
+    assert len(syms) >= 15, syms
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/mvg_b200.h but not exported"
+    assert set(_lib.SIGNATURES) | {"mvg_last_error", "mvg_abi_version", "mvg_launch_count"} == set(syms)
+    assert _lib.load().mvg_abi_version() == _lib.ABI_VERSION
+
+
+def test_ops_refuse_cpu_tensors():
+    """Same behaviour as the reference extension: 'Not implemented on the CPU'
+    (lib/models/ops/src/deform.h:49).  There is no CPU fallback to fall into."""
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        mvg.deform_forward(torch.zeros(1, 4, 8, 32), torch.tensor([[2, 2]]), torch.tensor([0]),
+                           torch.zeros(1, 1, 8, 1, 8, 2), torch.zeros(1, 1, 8, 1, 8), 64)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        mvg.multiview.triangulate_batch_of_points_batch_version(
+            torch.zeros(1, 2, 3, 4), torch.zeros(1, 2, 15, 2), None, solver="linalg")
+    pa = mvg.ProjAttn(256, 1, 8, 8, "ablation_not_use_rayconv")
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        pa(torch.zeros(1, 4, 256), torch.zeros(1, 4, 3, 2), [torch.zeros(1, 256, 4, 4)] * 3, None,
+           torch.tensor([[4, 4]] * 3), torch.tensor([0, 16, 32]))
+
+
+def test_unsupported_branches_raise():
+    with pytest.raises(NotImplementedError):
+        mvg.DQDecoderLayer([1, 1, 1], [0, 0, 0], [960, 512], 3, feature_update_method="attention",
+                           n_levels=1, n_points=8, open_forward_ffn=True,
+                           projattn_posembed_mode="ablation_not_use_rayconv")
+    with pytest.raises(NotImplementedError):
+        mvg.DQDecoderLayer([1, 1, 1], [0, 0, 0], [960, 512], 3, bayesian_update=True, n_levels=1,
+                           n_points=8, open_forward_ffn=True,
+                           projattn_posembed_mode="ablation_not_use_rayconv")
+    with pytest.raises(NotImplementedError):
+        mvg.DQDecoderLayer([1, 1, 1], [0, 0, 0], [960, 512], 3, triangulation_method="st",
+                           n_levels=1, n_points=8, open_forward_ffn=True,
+                           projattn_posembed_mode="ablation_not_use_rayconv")
+    pa = mvg.ProjAttn(256, 1, 8, 8, "use_rayconv")
+    with pytest.raises(NotImplementedError):
+        pa._check_supported()
+
+
+def test_camera_pack_matches_oracle_pieces():
+    from oracle import decoder_oracle as orc
+    for cfg in (syn.PANOPTIC, syn.SHELF):
+        sc = syn.make_scene(cfg, batch=2, n_views=4, num_instance=4, seed=3, levels=((4, 4),) * 3)
+        pk = cameras.pack_cameras(sc["meta"], sc["img_size"], use_cache=False)
+        assert pk.shape == (2, 4, _lib.MVG_CAM_FLOATS) and pk.dtype == torch.float32
+        P = orc.proj_matrices([m["camera"] for m in sc["meta"]])             # (B,V,3,4)
+        assert torch.allclose(pk[:, :, 33:45].reshape(2, 4, 3, 4), P, rtol=1e-6, atol=1e-3)
+        K = orc.calib_matrix([m["camera"] for m in sc["meta"]])
+        assert torch.allclose(pk[:, :, 45:54].reshape(2, 4, 3, 3), K.inverse(), rtol=1e-5, atol=1e-7)
+        for v, m in enumerate(sc["meta"]):
+            a = syn.affine_from_center_scale(m["center"][0].numpy(), m["scale"][0].numpy(), sc["img_size"])
+            assert np.allclose(pk[0, v, 21:27].numpy().reshape(2, 3), a, rtol=1e-6, atol=1e-5)
+            assert torch.allclose(pk[:, v, 27:33].reshape(2, 2, 3), m["inv_affine_trans"][:, :2].float())
+            assert torch.equal(pk[:, v, 54:56], (m["center"] * 2).float())
+            assert float(pk[0, v, 56]) == float((m["center"] * 2).max())
+
+
+def test_weight_packing_layout():
+    sc, sd = small_scene()
+    pa = mvg.ProjAttn(256, 1, 8, 8, "ablation_not_use_rayconv")
+    pa.load_state_dict({k[len("layers.0.proj_attn."):]: v for k, v in sd.items()
+                        if k.startswith("layers.0.proj_attn.")})
+    pk = pa.packed_weights()
+    assert pk["w_vg"].shape == (448, 256) and pk["w_vg"].dtype == torch.bfloat16
+    assert torch.equal(pk["w_vg"][:256].float(), pa.rayconv.weight.detach().to(torch.bfloat16).float())
+    assert torch.equal(pk["b_vg"][256:], torch.zeros(192))
+    assert torch.equal(pk["b_q"][:128], pa.sampling_offsets.bias.detach())
+    assert pa.packed_weights() is pk                      # cached
+    with torch.no_grad():
+        pa.rayconv.weight.mul_(2.0)
+    assert pa.packed_weights() is not pk                  # invalidated by the in-place update
