@@ -63,5 +63,9 @@ def robust_3d_stats(a, b, mask=None):
     if mask is not None:
         d = d[mask]
     if d.numel() == 0:
-        return dict(mean=0.0, median=0.0, max=0.0)
-    return dict(mean=float(d.mean()), median=float(d.median()), max=float(d.max()))
+        return dict(mean=0.0, median=0.0, max=0.0, q95=0.0, trimmed_mean=0.0)
+    ds = d.flatten().sort().values
+    keep = max(1, int(round(0.99 * ds.numel())))
+    return dict(mean=float(d.mean()), median=float(d.median()), max=float(d.max()),
+                q95=float(ds[min(ds.numel() - 1, int(0.95 * ds.numel()))]),
+                trimmed_mean=float(ds[:keep].mean()))
