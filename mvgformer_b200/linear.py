@@ -15,7 +15,7 @@ import torch.nn.functional as F
 
 from . import ops
 
-_BACKEND = os.environ.get("MVG_GEMM", "cublas")
+_BACKEND = os.environ.get("MVG_GEMM", "tcgen05")
 
 
 def set_backend(name: str) -> None:

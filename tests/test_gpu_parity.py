@@ -440,3 +440,53 @@ def test_full_size_properties():
     assert seen.sum() > 200, int(seen.sum())
     d = (refs0[0, 0] - scd["reference_points"][0]).norm(dim=-1)[seen]
     assert float(d.max()) < 1.0 and float(d.mean()) < 0.2, (float(d.max()), float(d.mean()))
+
+
+# ----------------------------------------------------------------------------- tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K,relu,out_dtype", [
+    (128, 128, 256, False, torch.bfloat16), (360, 256, 256, True, torch.bfloat16),
+    (1000, 448, 256, False, torch.bfloat16), (77, 192, 256, False, torch.float32),
+    (300, 16, 256, False, torch.float32), (513, 1024, 256, True, torch.bfloat16),
+    (257, 256, 1024, False, torch.bfloat16), (4096, 1792, 256, False, torch.bfloat16),
+    (129, 64, 64, False, torch.float32)])
+def test_linear_tcgen05(M, N, K, relu, out_dtype):
+    rng = np.random.default_rng(M + N + K)
+    a = torch.from_numpy(rng.standard_normal((M, K), dtype=np.float32)).to(DEV).bfloat16()
+    w = (torch.from_numpy(rng.standard_normal((N, K), dtype=np.float32)) / np.sqrt(K)).to(DEV).bfloat16()
+    b = torch.from_numpy(rng.standard_normal(N).astype(np.float32)).to(DEV)
+    out = ops.linear_bf16(a, w, b, relu=relu, out_dtype=out_dtype)
+    ref = a.double() @ w.double().t() + b.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    assert out.shape == (M, N) and out.dtype == out_dtype
+    tol = 2e-2 if out_dtype == torch.bfloat16 else 2e-4       # bf16 output rounding / fp32 accum
+    err = (out.double() - ref).abs().max()
+    assert err < tol, float(err)
+    # no bias, strided output (column block of a wider matrix)
+    wide = torch.full((M, N + 64), 7.0, dtype=out_dtype, device=DEV)
+    ops.linear_bf16(a, w, None, out_dtype=out_dtype, out=wide[:, :N])
+    assert (wide[:, :N].double() - a.double() @ w.double().t()).abs().max() < tol
+    assert (wide[:, N:] == 7.0).all()                           # nothing written past Nout
+
+
+def test_decoder_tcgen05_matches_cublas_backend():
+    """Whole decoder with the hand-written tcgen05 GEMMs vs the cuBLASLt library path."""
+    from mvgformer_b200 import linear as mlinear
+    sc, sd = small_scene()
+    scd = scene_to(sc, DEV)
+    dec = make_decoder(sc, sd, SMALL["num_layers"])
+    outs = {}
+    prev = mlinear.get_backend()
+    try:
+        for be in ("cublas", "tcgen05"):
+            mlinear.set_backend(be)
+            with torch.no_grad():
+                outs[be] = dec(scd["tgt"], scd["reference_points"], scd["src_views"], scd["meta"],
+                               scd["spatial_shapes"], scd["level_start_index"], None,
+                               query_pos=scd["query_pos"], threshold=SMALL["threshold"])
+    finally:
+        mlinear.set_backend(prev)
+    hs_c, refs_c, _, _, cls_c = outs["cublas"]
+    hs_t, refs_t, _, _, cls_t = outs["tcgen05"]
+    assert (hs_c[0] - hs_t[0]).abs().max() < 3e-2
+    assert (cls_c[0] - cls_t[0]).abs().max() < 3e-3
