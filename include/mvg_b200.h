@@ -99,12 +99,15 @@ MVG_API int mvg_pyramid_to_channels_last(const void* const* src_levels, int src_
  *   A (M,K) bf16 row-major, lda = K;  W (Nout,K) bf16 row-major (nn.Linear layout);
  *   bias (Nout) fp32 or NULL; out (M,Nout) bf16 or fp32 (`out_dtype`), row stride ldo
  *   elements.  relu != 0 applies max(0, .).  K % 64 == 0, Nout % 16 == 0.
+ *   row_mask (M) uint8 or NULL: rows with mask 0 are written as zeros (the `bounding` filter
+ *   of dq_decoder.py:585-586 fused into output_proj).
  * Used for: value/rayconv + the per-level sampling_offsets/attention_weights projections of
  * the raw pyramid (projattn.py:169,180-181), output_proj (:203), feature_update_mlp, FFN,
  * offset_net MLP (dq_decoder.py:101,284,289-292).
  */
 MVG_API int mvg_linear_bf16(const void* A, const void* W, const float* bias, void* out, int out_dtype,
-                    int64_t M, int Nout, int K, int64_t ldo, int relu, void* stream);
+                    int64_t M, int Nout, int K, int64_t ldo, int relu, const uint8_t* row_mask,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fused projection + projective attention sampling for all (b, v, n):

@@ -44,7 +44,7 @@ SIGNATURES = {
     "mvg_deform_forward": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "mvg_deform_backward": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "mvg_pyramid_to_channels_last": [_P, _I, _I, _P, _I, _I, _P, _P],
-    "mvg_linear_bf16": [_P, _P, _P, _P, _I, _L, _I, _I, _L, _I, _P],
+    "mvg_linear_bf16": [_P, _P, _P, _P, _I, _L, _I, _I, _L, _I, _P, _P],
     "mvg_project_sample_fused": [_P, _P, _P, _P, C.POINTER(MvgSampleParams), _P, _P, _P, _P, _P],
     "mvg_select_pad": [_P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "mvg_offsets_dlt": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P],

@@ -6,17 +6,17 @@
 //   rayconv / sampling_offsets / attention_weights on the pyramid (one launch for all L layers),
 //   the per-point qproj, output_proj, feature_update_mlp, FFN and the offset_net MLP.
 //
-// Structure (one CTA = one 128 x BLOCK_N output tile, 6 warps, warp-specialised):
-//   warp 0  TMA producer : cp.async.bulk.tensor (SWIZZLE_128B boxes of 64 K-elements) into a
-//                          kStages-deep shared-memory ring, mbarrier expect_tx / complete_tx
-//   warp 1  MMA issuer   : allocates TMEM, one thread issues tcgen05.mma.cta_group::1.kind::f16
-//                          (M=128, N=BLOCK_N, K=16) from shared-memory descriptors, tcgen05.commit
-//                          releases ring slots and finally signals the epilogue
-//   warps 2-5 epilogue   : tcgen05.ld (32 lanes x 16 columns) -> +bias -> ReLU -> convert ->
-//                          16-byte global stores; each warp owns the TMEM lane quarter warp%4
-// Two CTAs fit per SM (<= 98 KB smem, <= 128 TMEM columns each), so one CTA's epilogue overlaps
-// the other's main loop.  Tile order is N-fastest so the CTAs that share an A tile run together
-// and A is fetched from HBM once.
+// Structure (persistent, one CTA per SM, 10 warps, warp-specialised):
+//   warp 0  TMA producer : loads its weight chunk W[n0:n0+NC, :] once (<= 128 KB, stationary),
+//                          then streams 128 x 64 activation boxes (cp.async.bulk.tensor,
+//                          SWIZZLE_128B) through a 5-stage ring, mbarrier expect_tx/complete_tx
+//   warp 1  MMA issuer   : allocates all 512 TMEM columns (two NC-wide fp32 accumulators), one
+//                          thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=NC<=256,
+//                          K=16) from shared-memory descriptors; tcgen05.commit frees ring slots
+//                          and hands a finished accumulator to the epilogue
+//   warps 2-9 epilogue   : tcgen05.ld (32 lanes x 16 columns) -> +bias -> ReLU -> row mask ->
+//                          convert -> 16-byte global stores, overlapping the next tile's MMAs;
+//                          warp w may only touch TMEM lanes [32 (w%4), 32 (w%4) + 32)
 #include <cuda.h>
 
 #include "common.cuh"
@@ -105,49 +105,68 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 
-template <int BLOCK_N> struct GemmCfg {
-  static constexpr int kStages = (BLOCK_N >= 128) ? 3 : 4;
-  static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-};
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
-template <int BLOCK_N, typename OutT>
-__global__ void __launch_bounds__(kGemmThreads)
-linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                      const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ bias,
-                      OutT* __restrict__ out, int M, int N, int K, int64_t ldo, int relu) {
-  using Cfg = GemmCfg<BLOCK_N>;
+constexpr int kStages = 5;                       // A ring: 5 x (128 rows x 64 K) = 80 KB
+constexpr int kATileBytes = kBlockM * kBlockK * 2;
+constexpr int kMaxWBytes = 128 * 1024;           // stationary weight chunk
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreadsV2 = (2 + kEpiWarps) * 32;
+constexpr int kAccStride = 256;                  // TMEM columns between the two accumulators
+constexpr int kSmemBytesV2 = kMaxWBytes + kStages * kATileBytes + 1024 + 256;
+
+// Persistent, weight-stationary GEMM.  CTA c keeps the weight chunk  W[n0 : n0+NC, :]  resident in
+// shared memory (<= 128 KB) and streams 128-row activation tiles through a 5-stage TMA ring; the
+// accumulator is double-buffered in TMEM so the 8 epilogue warps drain tile i while the MMA warp
+// already issues tile i+1.  grid = n_chunks x groups; the CTAs of one group sweep the same M tiles
+// at the same time, so an A tile is read from HBM once and hit in L2 by the other chunks.
+template <typename OutT>
+__global__ void __launch_bounds__(kGemmThreadsV2, 1)
+linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                         const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ bias,
+                         const uint8_t* __restrict__ row_mask, OutT* __restrict__ out, int M, int N,
+                         int K, int NC, int n_chunks, int groups, int64_t ldo, int relu) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + Cfg::kStages;
-  uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 1);
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem + kMaxWBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kStages * kATileBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + kStages;
+  uint64_t* acc_full = bars + 2 * kStages;       // [2]
+  uint64_t* acc_empty = bars + 2 * kStages + 2;  // [2]
+  uint64_t* w_full = bars + 2 * kStages + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BLOCK_N;
-  const int m0 = blockIdx.y * kBlockM;
+  const int chunk = blockIdx.x % n_chunks;
+  const int group = blockIdx.x / n_chunks;
+  const int n0 = chunk * NC;
   const int num_kb = K / kBlockK;
+  const int m_tiles = (M + kBlockM - 1) / kBlockM;
+  const int w_kb_bytes = NC * kBlockK * 2;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], kEpiWarps);
+    }
+    mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM allocation is warp-collective; the same warp frees it
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
-                 "r"(static_cast<uint32_t>(Cfg::kTmemCols))
+                 "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -159,89 +178,116 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        uint8_t* sa = smem + s * Cfg::kStageBytes;
-        tma_load_2d(&tmap_a, &full_bar[s], sa, kb * kBlockK, m0);
-        tma_load_2d(&tmap_w, &full_bar[s], sa + Cfg::kABytes, kb * kBlockK, n0);
+      mbar_expect_tx(w_full, static_cast<uint32_t>(num_kb * w_kb_bytes));
+      for (int kb = 0; kb < num_kb; ++kb)
+        tma_load_2d(&tmap_w, w_full, smem_w + kb * w_kb_bytes, kb * kBlockK, n0);
+      uint32_t it = 0;
+      for (int mt = group; mt < m_tiles; mt += groups) {
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&a_empty[s], ph ^ 1);
+          mbar_expect_tx(&a_full[s], kATileBytes);
+          tma_load_2d(&tmap_a, &a_full[s], smem_a + s * kATileBytes, kb * kBlockK, mt * kBlockM);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_N);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      const uint32_t idesc = make_idesc_bf16(NC);
+      mbar_wait(w_full, 0);
+      uint32_t it = 0, i = 0;
+      for (int mt = group; mt < m_tiles; mt += groups, ++i) {
+        const uint32_t buf = i & 1;
+        mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint64_t da = make_smem_desc_sw128(sa);
-        const uint64_t db = make_smem_desc_sw128(sa + Cfg::kABytes);
+        const uint32_t tmem_d = tmem_base + buf * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&a_full[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + s * kATileBytes));
+          const uint64_t db = make_smem_desc_sw128(smem_u32(smem_w + kb * w_kb_bytes));
 #pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          // advance 16 K-elements = 32 B inside the 128 B swizzle row: +2 in the >>4 field
-          umma_bf16(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                    idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                      idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&a_empty[s]);
         }
-        umma_commit(&empty_bar[s]);            // frees the ring slot when these MMAs retire
+        umma_commit(&acc_full[buf]);
       }
-      umma_commit(tmem_full_bar);              // accumulator complete -> epilogue
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    OutT* orow = out + static_cast<int64_t>(row) * ldo + n0;
-#pragma unroll 2
-    for (int c = 0; c < BLOCK_N; c += 16) {
-      if (n0 + c >= N) break;                  // warp-uniform
-      uint32_t r[16];
-      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), r);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float v[16];
+    // ===================== epilogue (warps 2..9) =====================
+    const int e = warp - 2;
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int n_c16 = NC / 16;
+    const int c_begin = (e >> 2) == 0 ? 0 : (n_c16 + 1) / 2;
+    const int c_end = (e >> 2) == 0 ? (n_c16 + 1) / 2 : n_c16;
+    uint32_t i = 0;
+    for (int mt = group; mt < m_tiles; mt += groups, ++i) {
+      const uint32_t buf = i & 1;
+      mbar_wait(&acc_full[buf], (i >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = mt * kBlockM + q * 32 + lane;
+      const bool row_ok = row < M;
+      const bool keep = row_ok && (row_mask == nullptr || row_mask[row] != 0);
+      OutT* orow = out + static_cast<int64_t>(row) * ldo + n0;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride;
+      for (int cc = c_begin; cc < c_end; ++cc) {
+        const int c = cc * 16;
+        if (n0 + c >= N) break;                    // warp-uniform
+        uint32_t r[16];
+        tmem_ld16(taddr + static_cast<uint32_t>(c), r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-      if (bias != nullptr) {
+        for (int t = 0; t < 16; ++t) v[t] = __uint_as_float(r[t]);
+        if (bias != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + i));
-          v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          for (int t = 0; t < 16; t += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + t));
+            v[t] += b4.x; v[t + 1] += b4.y; v[t + 2] += b4.z; v[t + 3] += b4.w;
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) v[t] = fmaxf(v[t], 0.f);
+        }
+        if (!keep) {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) v[t] = 0.f;
+        }
+        if (row_ok) {
+          if constexpr (sizeof(OutT) == 2) {
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+            o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+            o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+            o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+            uint4* dst = reinterpret_cast<uint4*>(orow + c);
+            dst[0] = o0;
+            dst[1] = o1;
+          } else {
+            float4* dst = reinterpret_cast<float4*>(orow + c);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              dst[t] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+          }
         }
       }
-      if (relu) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-      }
-      if (row < M) {
-        if constexpr (sizeof(OutT) == 2) {
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
-          o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
-          o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
-          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-          uint4* dst = reinterpret_cast<uint4*>(orow + c);
-          dst[0] = o0;
-          dst[1] = o1;
-        } else {
-          float4* dst = reinterpret_cast<float4*>(orow + c);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(static_cast<uint32_t>(Cfg::kTmemCols))
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
                  : "memory");
   }
 }
@@ -286,28 +332,44 @@ static int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int K, int
   return MVG_OK;
 }
 
-template <int BLOCK_N, typename OutT>
-static int launch_linear(const void* A, const void* W, const float* bias, void* out, int64_t M,
-                         int Nout, int K, int64_t ldo, int relu, cudaStream_t st) {
-  using Cfg = GemmCfg<BLOCK_N>;
+template <typename OutT>
+static int launch_linear(const void* A, const void* W, const float* bias, const uint8_t* row_mask,
+                         void* out, int64_t M, int Nout, int K, int64_t ldo, int relu,
+                         cudaStream_t st) {
+  // weight chunk width: as wide as fits 128 KB / one UMMA (256), split evenly over the chunks
+  int nc_max = kMaxWBytes / (K * 2);
+  nc_max = nc_max > 256 ? 256 : (nc_max / 16) * 16;
+  if (nc_max < 16) {
+    set_error("mvg_linear_bf16: K=%d too large for the weight-stationary kernel", K);
+    return MVG_EUNSUPPORTED;
+  }
+  const int n_chunks = (Nout + nc_max - 1) / nc_max;
+  const int NC = (((Nout + n_chunks - 1) / n_chunks) + 15) / 16 * 16;
+  if (n_chunks > kNumSMs) {
+    set_error("mvg_linear_bf16: Nout=%d needs %d weight chunks (> %d SMs)", Nout, n_chunks, kNumSMs);
+    return MVG_EUNSUPPORTED;
+  }
+  const int m_tiles = static_cast<int>((M + kBlockM - 1) / kBlockM);
+  int groups = kNumSMs / n_chunks;
+  if (groups > m_tiles) groups = m_tiles;
   CUtensorMap ta, tw;
   int rc = make_tmap(&ta, A, M, K, kBlockM);
   if (rc) return rc;
-  rc = make_tmap(&tw, W, Nout, K, BLOCK_N);
+  rc = make_tmap(&tw, W, Nout, K, NC);
   if (rc) return rc;
-  auto kern = linear_tcgen05_kernel<BLOCK_N, OutT>;
+  auto kern = linear_tcgen05_ws_kernel<OutT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesV2);
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      set_error("cudaFuncSetAttribute(smem=%d): %s", kSmemBytesV2, cudaGetErrorString(e));
       return MVG_ELAUNCH;
     }
     attr_set = true;
   }
-  dim3 grid((Nout + BLOCK_N - 1) / BLOCK_N, static_cast<unsigned>((M + kBlockM - 1) / kBlockM));
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tw, bias, static_cast<OutT*>(out),
-                                                    static_cast<int>(M), Nout, K, ldo, relu);
+  kern<<<n_chunks * groups, kGemmThreadsV2, kSmemBytesV2, st>>>(
+      ta, tw, bias, row_mask, static_cast<OutT*>(out), static_cast<int>(M), Nout, K, NC, n_chunks,
+      groups, ldo, relu);
   return check_launch("mvg_linear_bf16");
 }
 
@@ -315,7 +377,7 @@ static int launch_linear(const void* A, const void* W, const float* bias, void* 
 
 extern "C" int mvg_linear_bf16(const void* A, const void* W, const float* bias, void* out,
                                int out_dtype, int64_t M, int Nout, int K, int64_t ldo, int relu,
-                               void* stream) {
+                               const uint8_t* row_mask, void* stream) {
   using namespace mvg;
   MVG_REQUIRE(A && W && out, "mvg_linear_bf16: null pointer");
   MVG_REQUIRE(M > 0 && M < (1ll << 31) && Nout > 0 && K > 0, "mvg_linear_bf16: empty shape");
@@ -330,14 +392,10 @@ extern "C" int mvg_linear_bf16(const void* A, const void* W, const float* bias, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (out_dtype == MVG_BF16) {
     MVG_REQUIRE(ldo % 8 == 0, "mvg_linear_bf16: ldo must be a multiple of 8 for bf16 output");
-    if (Nout <= 16) return launch_linear<16, __nv_bfloat16>(A, W, bias, out, M, Nout, K, ldo, relu, st);
-    if (Nout % 128 != 0 && Nout < 512) return launch_linear<64, __nv_bfloat16>(A, W, bias, out, M, Nout, K, ldo, relu, st);
-    return launch_linear<128, __nv_bfloat16>(A, W, bias, out, M, Nout, K, ldo, relu, st);
+    return launch_linear<__nv_bfloat16>(A, W, bias, row_mask, out, M, Nout, K, ldo, relu, st);
   } else if (out_dtype == MVG_F32) {
     MVG_REQUIRE(ldo % 4 == 0, "mvg_linear_bf16: ldo must be a multiple of 4 for fp32 output");
-    if (Nout <= 16) return launch_linear<16, float>(A, W, bias, out, M, Nout, K, ldo, relu, st);
-    if (Nout % 128 != 0 && Nout < 512) return launch_linear<64, float>(A, W, bias, out, M, Nout, K, ldo, relu, st);
-    return launch_linear<128, float>(A, W, bias, out, M, Nout, K, ldo, relu, st);
+    return launch_linear<float>(A, W, bias, row_mask, out, M, Nout, K, ldo, relu, st);
   }
   set_error("mvg_linear_bf16: unsupported out dtype %d", out_dtype);
   return MVG_EUNSUPPORTED;

@@ -21,44 +21,43 @@
 
 namespace mvg {
 
-constexpr int kWarps = 4;          // warps per CTA
-constexpr int kItemsPerWarp = 8;   // consecutive work items per warp per CTA iteration
+constexpr int kWarps = 16;         // warps per CTA; one persistent CTA per SM
 constexpr int kQP = 192;           // 128 offset channels + 64 logit channels per level
 constexpr int kHeads = 8;
 constexpr int kVgValueCols = 256;  // value columns precede the G columns in a vg row
-constexpr int kMaxNS = MVG_MAX_LEVELS * 8;
 
-struct WarpScratch {
-  float proj[MVG_MAX_LEVELS][kQP];        // per pyramid level: Linear outputs (offsets | logits)
-  float4 cw[kHeads * (kMaxNS + 1)];       // per (head, sample): 4 corner weights * attention
-  int base[kHeads * (kMaxNS + 1)];        // per (head, sample): texel offset | dx flag | dy flag
+template <int LV> struct WarpScratch {
+  float proj[LV][kQP];                    // per pyramid level: Linear outputs (offsets | logits)
+  float4 cw[kHeads * (LV * 8 + 1)];       // per (head, sample): 4 corner weights * attention
+  int base[kHeads * (LV * 8 + 1)];        // per (head, sample): texel offset | dx flag | dy flag
 };
 
 template <int LV>
-__global__ void __launch_bounds__(kWarps * 32, 4)
+__global__ void __launch_bounds__(kWarps * 32, 1)
 project_sample_kernel(const float* __restrict__ ref3d, const MvgCamera* __restrict__ cams,
                       const __nv_bfloat16* __restrict__ vg, const float* __restrict__ qproj,
                       const MvgSampleParams prm, __nv_bfloat16* __restrict__ sampled,
                       float* __restrict__ ref2d_out, uint8_t* __restrict__ bounding_out,
                       const float* __restrict__ refl_in) {
-  __shared__ WarpScratch scratch[kWarps];
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  WarpScratch& sc = scratch[warp];
+  WarpScratch<LV>& sc = reinterpret_cast<WarpScratch<LV>*>(smem_dyn)[warp];
   const int N = prm.points, V = prm.views, B = prm.batch;
   const int64_t total = static_cast<int64_t>(B) * V * N;
   const int ld = prm.ld_vg;
   constexpr int NS = LV * 8;           // samples per head
   constexpr int NSP = NS + 1;          // padded stride (bank-conflict-free across heads)
-  constexpr int kChunk = kWarps * kItemsPerWarp;
   const int m = lane >> 2, sub = lane & 3;
 
-  for (int64_t base_item = static_cast<int64_t>(blockIdx.x) * kChunk; base_item < total;
-       base_item += static_cast<int64_t>(gridDim.x) * kChunk) {
+  // Each CTA owns one contiguous range of (b, v, n) items; its 16 warps walk it together
+  // (warp w: first + w, first + w + 16, ...), so at any moment one SM works on ~one person's
+  // joints in one view and their overlapping sampling footprints share the SM's L1.
+  const int64_t first = total * blockIdx.x / gridDim.x;
+  const int64_t last = total * (blockIdx.x + 1) / gridDim.x;
+  {
 #pragma unroll 1
-    for (int it = 0; it < kItemsPerWarp; ++it) {
-      const int64_t item = base_item + warp + it * kWarps;
-      if (item >= total) break;
+    for (int64_t item = first + warp; item < last; item += kWarps) {
       const int n = static_cast<int>(item % N);
       const int bv = static_cast<int>(item / N);
       const int v = bv % V, b = bv / V;
@@ -295,18 +294,35 @@ extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, c
   MVG_REQUIRE(static_cast<int64_t>(s) * prm->ld_vg < (1ll << 29),
               "mvg_project_sample_fused: per-view map too large for 32-bit texel offsets");
   const int64_t total = static_cast<int64_t>(prm->batch) * prm->views * prm->points;
-  const int64_t chunks = (total + kWarps * kItemsPerWarp - 1) / (kWarps * kItemsPerWarp);
-  const int64_t max_grid = static_cast<int64_t>(kNumSMs) * 16;
-  const int grid = static_cast<int>(chunks < max_grid ? chunks : max_grid);
+  const int64_t per_cta = kWarps * 4;   // at least ~4 items per warp before spreading further
+  int64_t want = (total + per_cta - 1) / per_cta;
+  const int grid = static_cast<int>(want < kNumSMs ? (want < 1 ? 1 : want) : kNumSMs);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const MvgCamera* cam = reinterpret_cast<const MvgCamera*>(cams);
   const __nv_bfloat16* vgp = static_cast<const __nv_bfloat16*>(vg);
   __nv_bfloat16* sp = static_cast<__nv_bfloat16*>(sampled);
-  switch (prm->num_levels) {
-    case 1: project_sample_kernel<1><<<grid, kWarps * 32, 0, st>>>(ref3d, cam, vgp, qproj, *prm, sp, ref2d, bounding, refl_in); break;
-    case 2: project_sample_kernel<2><<<grid, kWarps * 32, 0, st>>>(ref3d, cam, vgp, qproj, *prm, sp, ref2d, bounding, refl_in); break;
-    case 3: project_sample_kernel<3><<<grid, kWarps * 32, 0, st>>>(ref3d, cam, vgp, qproj, *prm, sp, ref2d, bounding, refl_in); break;
-    default: project_sample_kernel<4><<<grid, kWarps * 32, 0, st>>>(ref3d, cam, vgp, qproj, *prm, sp, ref2d, bounding, refl_in); break;
+#define MVG_LAUNCH_PS(LV)                                                                       \
+  {                                                                                             \
+    constexpr int smem = kWarps * static_cast<int>(sizeof(WarpScratch<LV>));                    \
+    static bool attr_done = false;                                                              \
+    if (!attr_done) {                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(project_sample_kernel<LV>,                           \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
+      if (e != cudaSuccess) {                                                                   \
+        set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));                           \
+        return MVG_ELAUNCH;                                                                     \
+      }                                                                                         \
+      attr_done = true;                                                                         \
+    }                                                                                           \
+    project_sample_kernel<LV><<<grid, kWarps * 32, smem, st>>>(ref3d, cam, vgp, qproj, *prm, sp, \
+                                                               ref2d, bounding, refl_in);       \
   }
+  switch (prm->num_levels) {
+    case 1: MVG_LAUNCH_PS(1) break;
+    case 2: MVG_LAUNCH_PS(2) break;
+    case 3: MVG_LAUNCH_PS(3) break;
+    default: MVG_LAUNCH_PS(4) break;
+  }
+#undef MVG_LAUNCH_PS
   return check_launch("mvg_project_sample_fused");
 }

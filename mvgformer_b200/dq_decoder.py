@@ -223,8 +223,8 @@ class DQDecoderLayer(nn.Module):
             sampled, ref2d, bounding = ops.project_sample_fused(ref3d, ctx.cams, vg, qproj, prm)
         # 4. output_proj, mask, view-mean, update MLP, LN, FFN, LN
         with prof.stage("output_proj"):
-            attn = linear(sampled, pw["w_o"], pw["b_o"])                          # (B,V,N,256) bf16
-            attn = attn * bounding.unsqueeze(-1).to(attn.dtype)                   # :585-586
+            # (B,V,N,256) bf16, rows of out-of-view points zeroed in the epilogue (:585-586)
+            attn = linear(sampled, pw["w_o"], pw["b_o"], row_mask=bounding)
         with prof.stage("update_feature"):
             aver = ops.masked_view_mean(attn, bounding)                           # :770
             t2 = linear(aver, lw["w_fu"], lw["b_fu"])

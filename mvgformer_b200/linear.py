@@ -30,12 +30,13 @@ def get_backend() -> str:
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, relu: bool = False,
-           out_dtype=torch.bfloat16) -> torch.Tensor:
-    """x (..., K) bf16, w (Nout, K) bf16, bias (Nout) fp32|None."""
+           out_dtype=torch.bfloat16, row_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x (..., K) bf16, w (Nout, K) bf16, bias (Nout) fp32|None, row_mask (rows) uint8|None."""
     if not x.is_cuda:
         raise RuntimeError("Not implemented on the CPU")
     if _BACKEND == "tcgen05":
-        return ops.linear_bf16(x.contiguous(), w, bias, relu=relu, out_dtype=out_dtype)
+        return ops.linear_bf16(x.contiguous(), w, bias, relu=relu, out_dtype=out_dtype,
+                               row_mask=row_mask)
     # library path: bf16 x bf16 -> fp32 out (cuBLASLt), bias / activation in fp32
     x2 = x.reshape(-1, x.shape[-1])
     y = torch.mm(x2, w.t(), out_dtype=torch.float32)
@@ -43,4 +44,6 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, re
         y = y + bias
     if relu:
         y = F.relu(y)
+    if row_mask is not None:
+        y = y * row_mask.reshape(-1, 1).to(y.dtype)
     return y.to(out_dtype).view(x.shape[:-1] + (w.shape[0],))

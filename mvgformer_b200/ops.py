@@ -33,7 +33,8 @@ def pyramid_to_channels_last(src_views: Sequence[torch.Tensor]) -> torch.Tensor:
 
 def linear_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *,
                 relu: bool = False, out_dtype=torch.bfloat16,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None,
+                row_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = act(a @ w^T + bias) on tcgen05.  a (..., K) bf16 contiguous, w (Nout, K) bf16."""
     lib = _lib.load()
     K = a.shape[-1]
@@ -43,7 +44,7 @@ def linear_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
         out = torch.empty(a.shape[:-1] + (nout,), dtype=out_dtype, device=a.device)
     check(lib.mvg_linear_bf16(a.data_ptr(), w.data_ptr(), _lib.ptr(bias), out.data_ptr(),
                               dtype_code(out.dtype), M, nout, K, out.stride(-2) if out.dim() > 1 else nout,
-                              1 if relu else 0, stream_ptr(a.device)), "mvg_linear_bf16")
+                              1 if relu else 0, _lib.ptr(row_mask), stream_ptr(a.device)), "mvg_linear_bf16")
     return out
 
 

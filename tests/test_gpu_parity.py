@@ -448,7 +448,8 @@ def test_full_size_properties():
     (1000, 448, 256, False, torch.bfloat16), (77, 192, 256, False, torch.float32),
     (300, 16, 256, False, torch.float32), (513, 1024, 256, True, torch.bfloat16),
     (257, 256, 1024, False, torch.bfloat16), (4096, 1792, 256, False, torch.bfloat16),
-    (129, 64, 64, False, torch.float32)])
+    (129, 64, 64, False, torch.float32), (76800, 256, 256, False, torch.bfloat16),
+    (2000, 224, 1024, True, torch.bfloat16)])
 def test_linear_tcgen05(M, N, K, relu, out_dtype):
     rng = np.random.default_rng(M + N + K)
     a = torch.from_numpy(rng.standard_normal((M, K), dtype=np.float32)).to(DEV).bfloat16()
@@ -467,6 +468,10 @@ def test_linear_tcgen05(M, N, K, relu, out_dtype):
     ops.linear_bf16(a, w, None, out_dtype=out_dtype, out=wide[:, :N])
     assert (wide[:, :N].double() - a.double() @ w.double().t()).abs().max() < tol
     assert (wide[:, N:] == 7.0).all()                           # nothing written past Nout
+    # row mask fused in the epilogue (bounding filter of output_proj)
+    mask = torch.from_numpy(rng.integers(0, 2, size=M).astype(np.uint8)).to(DEV)
+    outm = ops.linear_bf16(a, w, b, relu=relu, out_dtype=out_dtype, row_mask=mask)
+    assert torch.equal(outm, out * mask[:, None].to(out.dtype))
 
 
 def test_decoder_tcgen05_matches_cublas_backend():
