@@ -62,6 +62,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
@@ -109,13 +115,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int kStages = 5;                       // A ring: 5 x (128 rows x 64 K) = 80 KB
+constexpr int kStages = 4;                       // A ring: 4 x (128 rows x 64 K) = 64 KB
 constexpr int kATileBytes = kBlockM * kBlockK * 2;
 constexpr int kMaxWBytes = 128 * 1024;           // stationary weight chunk
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreadsV2 = (2 + kEpiWarps) * 32;
 constexpr int kAccStride = 256;                  // TMEM columns between the two accumulators
-constexpr int kSmemBytesV2 = kMaxWBytes + kStages * kATileBytes + 1024 + 256;
+constexpr int kStageOutBytes = 32 * 128;         // per epilogue warp: 32 rows x 128 B, SWIZZLE_128B
+constexpr int kSmemBytesV2 = kMaxWBytes + kStages * kATileBytes + kEpiWarps * kStageOutBytes + 1024 + 256;
 
 // Persistent, weight-stationary GEMM.  CTA c keeps the weight chunk  W[n0 : n0+NC, :]  resident in
 // shared memory (<= 128 KB) and streams 128-row activation tiles through a 5-stage TMA ring; the
@@ -125,7 +132,9 @@ constexpr int kSmemBytesV2 = kMaxWBytes + kStages * kATileBytes + 1024 + 256;
 template <typename OutT>
 __global__ void __launch_bounds__(kGemmThreadsV2, 1)
 linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                         const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ bias,
+                         const __grid_constant__ CUtensorMap tmap_w,
+                         const __grid_constant__ CUtensorMap tmap_out, int use_tma_store,
+                         const float* __restrict__ bias,
                          const uint8_t* __restrict__ row_mask, OutT* __restrict__ out, int M, int N,
                          int K, int NC, int n_chunks, int groups, int64_t ldo, int relu) {
   extern __shared__ uint8_t smem_raw[];
@@ -133,7 +142,8 @@ linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + kMaxWBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kStages * kATileBytes);
+  uint8_t* smem_out = smem_a + kStages * kATileBytes;              // 1024-aligned staging tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + kEpiWarps * kStageOutBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + kStages;
   uint64_t* acc_full = bars + 2 * kStages;       // [2]
@@ -223,10 +233,89 @@ linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ===================== epilogue (warps 2..9) =====================
     const int e = warp - 2;
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    uint32_t i = 0;
+    if (use_tma_store) {
+      // TMEM -> registers -> swizzled smem tile (32 rows x 128 B) -> cp.async.bulk.tensor store.
+      constexpr int kUnitCols = 128 / static_cast<int>(sizeof(OutT));   // 64 bf16 / 32 fp32
+      uint8_t* stage = smem_out + e * kStageOutBytes;
+      const int n_units = NC / kUnitCols;
+      const int u_begin = (e >> 2) == 0 ? 0 : (n_units + 1) / 2;
+      const int u_end = (e >> 2) == 0 ? (n_units + 1) / 2 : n_units;
+      for (int mt = group; mt < m_tiles; mt += groups, ++i) {
+        const uint32_t buf = i & 1;
+        mbar_wait(&acc_full[buf], (i >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row0 = mt * kBlockM + q * 32;
+        const int row = row0 + lane;
+        const bool keep = row < M && (row_mask == nullptr || row_mask[row] != 0);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccStride;
+        for (int u = u_begin; u < u_end; ++u) {
+          const int c0 = u * kUnitCols;
+          if (n0 + c0 >= N) break;                 // warp-uniform
+          // the previous bulk store must have finished READING the staging tile
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int h = 0; h < kUnitCols / 32; ++h) {
+            uint32_t r[32];
+            tmem_ld16(taddr + static_cast<uint32_t>(c0 + h * 32), r);
+            tmem_ld16(taddr + static_cast<uint32_t>(c0 + h * 32 + 16), r + 16);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float v[32];
+#pragma unroll
+            for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]);
+            if (bias != nullptr) {
+#pragma unroll
+              for (int t = 0; t < 32; t += 4) {
+                const int col = n0 + c0 + h * 32 + t;
+                if (col < N) {                     // N % 16 == 0: whole float4 in or out
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+                  v[t] += b4.x; v[t + 1] += b4.y; v[t + 2] += b4.z; v[t + 3] += b4.w;
+                }
+              }
+            }
+            if (relu) {
+#pragma unroll
+              for (int t = 0; t < 32; ++t) v[t] = fmaxf(v[t], 0.f);
+            }
+            if (!keep) {
+#pragma unroll
+              for (int t = 0; t < 32; ++t) v[t] = 0.f;
+            }
+            uint8_t* srow = stage + lane * 128;
+            if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {        // 4 chunks of 8 bf16
+                uint4 o;
+                o.x = pack_bf16x2(v[8 * t], v[8 * t + 1]);     o.y = pack_bf16x2(v[8 * t + 2], v[8 * t + 3]);
+                o.z = pack_bf16x2(v[8 * t + 4], v[8 * t + 5]); o.w = pack_bf16x2(v[8 * t + 6], v[8 * t + 7]);
+                const int j = h * 4 + t;
+                *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = o;
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {        // 8 chunks of 4 fp32
+                const float4 o = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+                *reinterpret_cast<float4*>(srow + ((t ^ (lane & 7)) << 4)) = o;
+              }
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, stage, n0 + c0, row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
     const int n_c16 = NC / 16;
     const int c_begin = (e >> 2) == 0 ? 0 : (n_c16 + 1) / 2;
     const int c_end = (e >> 2) == 0 ? (n_c16 + 1) / 2 : n_c16;
-    uint32_t i = 0;
     for (int mt = group; mt < m_tiles; mt += groups, ++i) {
       const uint32_t buf = i & 1;
       mbar_wait(&acc_full[buf], (i >> 1) & 1);
@@ -282,6 +371,7 @@ linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a,
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -332,6 +422,31 @@ static int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int K, int
   return MVG_OK;
 }
 
+// Output tensor map for the epilogue's bulk stores: (rows, cols) row-major with row stride ldo,
+// box = (128 bytes of columns, 32 rows), 128-byte swizzle (matches the staging tile).
+static int make_out_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int cols, int64_t ldo,
+                         int elem_size) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return MVG_ELAUNCH;
+  }
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldo) * elem_size};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_size), 32};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, elem_size == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                   2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(out) failed (%d) rows=%lld cols=%d ldo=%lld", static_cast<int>(r),
+              static_cast<long long>(rows), cols, static_cast<long long>(ldo));
+    return MVG_ELAUNCH;
+  }
+  return MVG_OK;
+}
+
 template <typename OutT>
 static int launch_linear(const void* A, const void* W, const float* bias, const uint8_t* row_mask,
                          void* out, int64_t M, int Nout, int K, int64_t ldo, int relu,
@@ -344,7 +459,12 @@ static int launch_linear(const void* A, const void* W, const float* bias, const 
     return MVG_EUNSUPPORTED;
   }
   const int n_chunks = (Nout + nc_max - 1) / nc_max;
-  const int NC = (((Nout + n_chunks - 1) / n_chunks) + 15) / 16 * 16;
+  // bulk-store epilogue works in units of 128 B of columns; narrow outputs use direct stores
+  constexpr int kUnit = 128 / static_cast<int>(sizeof(OutT));
+  const int use_tma_store = (Nout >= kUnit && nc_max >= kUnit) ? 1 : 0;
+  const int gran = use_tma_store ? kUnit : 16;
+  int NC = (((Nout + n_chunks - 1) / n_chunks) + gran - 1) / gran * gran;
+  if (NC > nc_max) NC = nc_max;
   if (n_chunks > kNumSMs) {
     set_error("mvg_linear_bf16: Nout=%d needs %d weight chunks (> %d SMs)", Nout, n_chunks, kNumSMs);
     return MVG_EUNSUPPORTED;
@@ -357,6 +477,13 @@ static int launch_linear(const void* A, const void* W, const float* bias, const 
   if (rc) return rc;
   rc = make_tmap(&tw, W, Nout, K, NC);
   if (rc) return rc;
+  CUtensorMap tout;
+  if (use_tma_store) {
+    rc = make_out_tmap(&tout, out, M, Nout, ldo, static_cast<int>(sizeof(OutT)));
+    if (rc) return rc;
+  } else {
+    tout = ta;   // unused by the kernel
+  }
   auto kern = linear_tcgen05_ws_kernel<OutT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -368,8 +495,8 @@ static int launch_linear(const void* A, const void* W, const float* bias, const 
     attr_set = true;
   }
   kern<<<n_chunks * groups, kGemmThreadsV2, kSmemBytesV2, st>>>(
-      ta, tw, bias, row_mask, static_cast<OutT*>(out), static_cast<int>(M), Nout, K, NC, n_chunks,
-      groups, ldo, relu);
+      ta, tw, tout, use_tma_store, bias, row_mask, static_cast<OutT*>(out), static_cast<int>(M), Nout,
+      K, NC, n_chunks, groups, ldo, relu);
   return check_launch("mvg_linear_bf16");
 }
 

@@ -26,10 +26,33 @@ constexpr int kQP = 192;           // 128 offset channels + 64 logit channels pe
 constexpr int kHeads = 8;
 constexpr int kVgValueCols = 256;  // value columns precede the G columns in a vg row
 
+// acc (two fp32 packed in a 64-bit register) += {w, w} * {bf16 lo, bf16 hi} of the 32-bit word u
+// (Blackwell packed FFMA2: one issue slot for two channels).
+__device__ __forceinline__ void fma2_bf16pair(uint64_t& acc, uint32_t u, uint64_t ww) {
+  uint64_t v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(u << 16), "r"(u & 0xffff0000u));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(v), "l"(ww));
+}
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
+  return v;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ void fma2_corner(uint64_t (&acc)[4], const uint4& c, float w) {
+  const uint64_t ww = pack2(w, w);
+  fma2_bf16pair(acc[0], c.x, ww);
+  fma2_bf16pair(acc[1], c.y, ww);
+  fma2_bf16pair(acc[2], c.z, ww);
+  fma2_bf16pair(acc[3], c.w, ww);
+}
+
 template <int LV> struct WarpScratch {
   float proj[LV][kQP];                    // per pyramid level: Linear outputs (offsets | logits)
-  float4 cw[kHeads * (LV * 8 + 1)];       // per (head, sample): 4 corner weights * attention
-  int base[kHeads * (LV * 8 + 1)];        // per (head, sample): texel offset | dx flag | dy flag
+  float4 cw[LV * 8 * kHeads];             // [sample][head]: 4 corner weights * attention
+  int base[LV * 8 * kHeads];              // [sample][head]: 16-byte offset of corner 00 | dx | dy
 };
 
 template <int LV>
@@ -46,8 +69,8 @@ project_sample_kernel(const float* __restrict__ ref3d, const MvgCamera* __restri
   const int N = prm.points, V = prm.views, B = prm.batch;
   const int64_t total = static_cast<int64_t>(B) * V * N;
   const int ld = prm.ld_vg;
+  const uint32_t ld16 = static_cast<uint32_t>(prm.ld_vg) >> 3;   // row stride in 16-byte units
   constexpr int NS = LV * 8;           // samples per head
-  constexpr int NSP = NS + 1;          // padded stride (bank-conflict-free across heads)
   const int m = lane >> 2, sub = lane & 3;
 
   // Each CTA owns one contiguous range of (b, v, n) items; its 16 warps walk it together
@@ -148,19 +171,15 @@ project_sample_kernel(const float* __restrict__ ref3d, const MvgCamera* __restri
         }
 #pragma unroll
         for (int l = 0; l < LV; ++l) {
-          float acc[8], t[8];
-          unpack8(cn[l][0], t);
+          uint64_t a2[4] = {pack2(qv[0], qv[1]), pack2(qv[2], qv[3]), pack2(qv[4], qv[5]), pack2(qv[6], qv[7])};
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = cwgt[l][0] * t[i];
+          for (int c = 0; c < 4; ++c) fma2_corner(a2, cn[l][c], cwgt[l][c]);
+          float r8[8];
 #pragma unroll
-          for (int c = 1; c < 4; ++c) {
-            unpack8(cn[l][c], t);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] += cwgt[l][c] * t[i];
-          }
+          for (int i = 0; i < 4; ++i) unpack2(a2[i], r8[2 * i], r8[2 * i + 1]);
           float4* dst = reinterpret_cast<float4*>(&sc.proj[l][lane * 8]);
-          dst[0] = make_float4(acc[0] + qv[0], acc[1] + qv[1], acc[2] + qv[2], acc[3] + qv[3]);
-          dst[1] = make_float4(acc[4] + qv[4], acc[5] + qv[5], acc[6] + qv[6], acc[7] + qv[7]);
+          dst[0] = make_float4(r8[0], r8[1], r8[2], r8[3]);
+          dst[1] = make_float4(r8[4], r8[5], r8[6], r8[7]);
         }
       }
       __syncwarp();
@@ -216,50 +235,43 @@ project_sample_kernel(const float* __restrict__ ref3d, const MvgCamera* __restri
           cwv.y = (okh0 && okw1) ? hh * lw * wgt : 0.f;
           cwv.z = (okh1 && okw0) ? lh * hw * wgt : 0.f;
           cwv.w = (okh1 && okw1) ? lh * lw * wgt : 0.f;
-          // texel index of the (ha, wa) corner; bit0: +1 texel for the right column exists,
-          // bit1: +W texels for the lower row exists (otherwise the clamped corner aliases).
+          // offset (16-byte units) of the (ha, wa) corner; bit0: a right column exists (+1 texel),
+          // bit1: a lower row exists (+W texels); otherwise the clamped corner aliases.
           const int tex = start + ha * W + wa;
-          sc.cw[m * NSP + r] = cwv;
-          sc.base[m * NSP + r] = (tex << 2) | ((wb > wa) ? 1 : 0) | ((hb > ha) ? 2 : 0);
+          sc.cw[r * kHeads + m] = cwv;
+          sc.base[r * kHeads + m] = ((tex * ld16) << 2) | ((wb > wa) ? 1 : 0) | ((hb > ha) ? 2 : 0);
         }
       }
       __syncwarp();
 
       // ---------------- phase C (a5): gather 4 corners x NS samples, 8 channels per lane
-      float acc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      const __nv_bfloat16* vlane = vrow + m * 32 + sub * 8;
+      uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};     // 8 fp32 accumulators as 4 packed pairs
+      const uint4* vlane16 = reinterpret_cast<const uint4*>(vrow + m * 32 + sub * 8);
 #pragma unroll
       for (int l = 0; l < LV; ++l) {
-        const int64_t rowstep = static_cast<int64_t>(prm.level_w[l]) * ld;
+        const uint32_t rowstep16 = static_cast<uint32_t>(prm.level_w[l]) * ld16;
 #pragma unroll 4
         for (int p = 0; p < 8; ++p) {
           const int r = l * 8 + p;
-          const float4 cwv = sc.cw[m * NSP + r];
-          const int bs = sc.base[m * NSP + r];
-          const __nv_bfloat16* p00 = vlane + static_cast<int64_t>(bs >> 2) * ld;
-          const int64_t dxo = (bs & 1) ? ld : 0;
-          const int64_t dyo = (bs & 2) ? rowstep : 0;
-          const uint4 c1 = ldg_nc_v4(p00);
-          const uint4 c2 = ldg_nc_v4(p00 + dxo);
-          const uint4 c3 = ldg_nc_v4(p00 + dyo);
-          const uint4 c4 = ldg_nc_v4(p00 + dyo + dxo);
-          float t[8];
-          unpack8(c1, t);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += cwv.x * t[i];
-          unpack8(c2, t);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += cwv.y * t[i];
-          unpack8(c3, t);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += cwv.z * t[i];
-          unpack8(c4, t);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += cwv.w * t[i];
+          const float4 cwv = sc.cw[r * kHeads + m];
+          const uint32_t bs = static_cast<uint32_t>(sc.base[r * kHeads + m]);
+          const uint32_t o00 = bs >> 2;
+          const uint32_t o01 = o00 + ((bs & 1u) ? ld16 : 0u);
+          const uint32_t o10 = o00 + ((bs & 2u) ? rowstep16 : 0u);
+          const uint32_t o11 = o10 + ((bs & 1u) ? ld16 : 0u);
+          const uint4 c1 = __ldg(vlane16 + o00);
+          const uint4 c2 = __ldg(vlane16 + o01);
+          const uint4 c3 = __ldg(vlane16 + o10);
+          const uint4 c4 = __ldg(vlane16 + o11);
+          fma2_corner(acc2, c1, cwv.x);
+          fma2_corner(acc2, c2, cwv.y);
+          fma2_corner(acc2, c3, cwv.z);
+          fma2_corner(acc2, c4, cwv.w);
         }
       }
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) unpack2(acc2[i], acc[2 * i], acc[2 * i + 1]);
       uint4 o;
       o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
       o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
@@ -291,7 +303,7 @@ extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, c
   }
   MVG_REQUIRE(s == prm->spatial_size, "mvg_project_sample_fused: spatial_size %d != sum H*W %d",
               prm->spatial_size, s);
-  MVG_REQUIRE(static_cast<int64_t>(s) * prm->ld_vg < (1ll << 29),
+  MVG_REQUIRE(static_cast<int64_t>(s) * (prm->ld_vg / 8) < (1ll << 29),
               "mvg_project_sample_fused: per-view map too large for 32-bit texel offsets");
   const int64_t total = static_cast<int64_t>(prm->batch) * prm->views * prm->points;
   const int64_t per_cta = kWarps * 4;   // at least ~4 items per warp before spreading further
