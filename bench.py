@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--gemm", default=None, choices=[None, "tcgen05", "cublas"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -228,19 +229,33 @@ def run_ours(a):
              "scale": m["scale"].to(dev), "inv_affine_trans": m["inv_affine_trans"].to(dev)}
             for m in sc["meta"]]
     shapes, lsi = sc["spatial_shapes"].to(dev), sc["level_start_index"].to(dev)
-    shard = (rank, world, None) if world > 1 else None
     ql = (sharding.shard_bounds(Q, rank, world)[1] - sharding.shard_bounds(Q, rank, world)[0]) if world > 1 else Q
 
-    def forward(inp, fts):
+    def forward(inp, fts, check=False):
         with torch.no_grad():
+            if world > 1:
+                # one NCCL all-gather of poses + scores (+ per-layer counts) per step
+                res = sharding.sharded_decoder_forward(
+                    dec, inp["tgt"], inp["reference_points"], fts, meta, shapes, lsi, inp["query_pos"],
+                    threshold=a.threshold, num_queries=Q, joints=J, rank=rank, world=world, check=check)
+                return res[0], res[1]
             hs, refs, refs2d, proj2d, cls = dec(inp["tgt"], inp["reference_points"], fts, meta, shapes,
                                                 lsi, None, query_pos=inp["query_pos"],
-                                                threshold=a.threshold, shard=shard)
-            poses, prob = refs[-1], cls[-1]
-            if world > 1:
-                poses = sharding.allgather_queries(poses, Q, J, world)
-                prob = sharding.allgather_queries(prob, Q, 1, world)
-        return poses, prob
+                                                threshold=a.threshold)
+            return refs[-1], cls[-1]
+
+    graphed = None
+    if not a.no_graph:
+        from mvgformer_b200.graphs import GraphedDecoder
+        graphed = GraphedDecoder(dec, d["tgt"], d["reference_points"], feats, meta, shapes, lsi,
+                                 d["query_pos"], threshold=a.threshold,
+                                 shard=(rank, world, None) if world > 1 else None, num_queries=Q, joints=J)
+
+    def forward_resident():
+        if graphed is not None:
+            out = graphed()
+            return out[0], out[1]
+        return forward(d, feats)
 
     def barrier():
         if world > 1:
@@ -263,17 +278,30 @@ def run_ours(a):
 
     # ---- device-resident throughput
     for _ in range(max(a.warmup, 3)):
-        forward(d, feats)
+        forward_resident()
     clocks = ClockSampler(local)
     clocks.start()
+    total_ms = timed(forward_resident, a.steps)
+    if graphed is not None and graphed.empty_scene_layers():
+        raise SystemExit("bench: empty-scene slow path hit on synthetic data (unexpected)")
+    prof.enable(False)
+    clk = clocks.stop()
+    # libmvg_b200 launches per step and per-stage CUDA-event times: measured on an eager pass
+    # of the same step (events cannot be recorded inside a replayed graph)
+    for _ in range(3):
+        forward(d, feats)
+    torch.cuda.synchronize()
     prof.reset()
     prof.enable(True)
     n0 = _lib.launch_count()
-    total_ms = timed(lambda: forward(d, feats), a.steps)
-    launches = (_lib.launch_count() - n0) // max(a.steps, 1)
+    n_prof = max(3, min(a.steps, 10))
+    for _ in range(n_prof):
+        forward(d, feats)
+    torch.cuda.synchronize()
+    launches_per_step = (_lib.launch_count() - n0) // n_prof
     prof.enable(False)
-    clk = clocks.stop()
     stages = prof.summary()
+    prof_steps = n_prof
     value = B * Q * a.steps / (total_ms * 1e-3)
 
     # ---- end to end: pinned host buffers in, poses + scores out, every step
@@ -284,12 +312,18 @@ def run_ours(a):
         out_prob = torch.empty((B, Q, 2), dtype=torch.float32).pin_memory()
 
         def e2e_step():
-            inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            fts = [s.to(dev, non_blocking=True) for s in host_feats]
-            poses, prob = forward(inp, fts)
+            if graphed is not None:      # H2D into the graph's static inputs, replay, D2H
+                out = graphed(host["tgt"], host["reference_points"], host_feats, host["query_pos"])
+                poses, prob = out[0], out[1]
+            else:
+                inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+                fts = [s.to(dev, non_blocking=True) for s in host_feats]
+                poses, prob = forward(inp, fts, check=True)   # result consumed on the host
             out_pose.copy_(poses, non_blocking=True)
             out_prob.copy_(prob, non_blocking=True)
             torch.cuda.current_stream().synchronize()     # the caller consumes the result
+            if graphed is not None and world > 1 and graphed.empty_scene_layers():
+                forward(d, feats, check=True)             # exact slow path (never on this data)
 
         for _ in range(3):
             e2e_step()
@@ -323,7 +357,7 @@ def run_ours(a):
                 "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "algorithmic_bytes_per_launch": int(alg_bytes),
                 "launch_ms": st["mean_ms"], "launches_timed": st["count"], "peak_source": peak_src,
-                "stage_ms_per_step": {k: v["total_ms"] / a.steps for k, v in sorted(stages.items())}}
+                "stage_ms_per_step": {k: v["total_ms"] / prof_steps for k, v in sorted(stages.items())}}
 
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -337,7 +371,8 @@ def run_ours(a):
             "warmup": max(a.warmup, 3), "ms_per_step": total_ms / a.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(a, world),
-            "gemm_backend": mlinear.get_backend(), "gpu_launches": int(launches),
+            "gemm_backend": mlinear.get_backend(), "gpu_launches": int(launches_per_step),
+            "launch_mode": "eager" if graphed is None else "cuda-graph replay",
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         }
         print(json.dumps(line), flush=True)

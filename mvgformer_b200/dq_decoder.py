@@ -244,9 +244,14 @@ class DQDecoderLayer(nn.Module):
         else:
             method = "threshold" if self.filter_query else "all"
             selected, _, info = ops.select_pad(prob, threshold, method, min_one=shard is None)
-            if shard is not None:                    # (rank, world, group): global :620-623 rule
-                from .sharding import apply_global_min_one
-                selected = apply_global_min_one(selected, info, shard[0], shard[2])
+            if shard is not None:
+                # (rank, world, group, force): the "always one query" rule (:620-623) is global.
+                # No per-layer collective: the local count is returned and checked after the
+                # final all-gather (sharding.gather_results); `force` marks a re-run in which
+                # rank 0 applies the rule for this layer.
+                self._shard_count = info[0:1]
+                if len(shard) > 3 and shard[3] and shard[0] == 0:
+                    selected[0, 0] = 1
         # 6. offset_net MLP per view
         with prof.stage("offset_mlp"):
             h = attn
@@ -302,25 +307,33 @@ class DQDecoder(nn.Module):
                 src_level_start_index, src_valid_ratios, query_pos=None, src_padding_mask=None,
                 rgb_views=None, output_dir='./', frame_id=None, indices=None, threshold=0.5,
                 indices_all=None, shard=None):
-        """dq_decoder.py:1107-1172.  Extension: `shard=(rank, world, group)` runs this rank's
-        contiguous query block (tgt / reference_points / query_pos already sliced with
-        sharding.shard_points); the caller all-gathers the returned poses."""
+        """dq_decoder.py:1107-1172.  Extension: `shard=(rank, world, group[, forced_layers])` runs
+        this rank's contiguous query block (tgt / reference_points / query_pos already sliced
+        with sharding.shard_points); sharding.sharded_decoder_forward gathers the poses."""
         if not tgt.is_cuda:
             raise RuntimeError("Not implemented on the CPU")
         ctx = DecoderContext(src_views, meta, self.layers[0].img_size, list(self.layers), tgt.shape[0])
         output = tgt
         inter, inter_ref, inter_2d, inter_proj, classes = [], [], [], [], []
         ref_points_2d = None
-        for layer in self.layers:
+        counts = []
+        for lid, layer in enumerate(self.layers):
+            lshard = shard
+            if shard is not None:
+                force = len(shard) > 3 and shard[3] is not None and lid in shard[3]
+                lshard = (shard[0], shard[1], shard[2], force)
             output, reference_points, ref_points_2d, projs_2d_absolute, outputs_class = \
                 layer._forward_ctx(output, query_pos, reference_points, ctx, threshold=threshold,
-                                   indices=indices, shard=shard)
+                                   indices=indices, shard=lshard)
+            if shard is not None:
+                counts.append(layer._shard_count)
             if self.return_intermediate:
                 inter.append(output)
                 inter_ref.append(reference_points)
                 inter_2d.append(ref_points_2d)
                 inter_proj.append(projs_2d_absolute)
                 classes.append(outputs_class)
+        self.last_shard_counts = torch.cat(counts) if counts else None     # (L,) int32, device
         if self.return_intermediate:
             return torch.stack(inter), torch.stack(inter_ref), torch.stack(inter_2d), \
                 torch.stack(inter_proj), classes

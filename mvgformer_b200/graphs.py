@@ -1,0 +1,78 @@
+"""CUDA-graph capture of the whole L-layer decoder call (no tracing compiler involved).
+
+The decoder forward enqueues ~70 kernels with no host synchronisation, data-dependent shapes
+or allocations that escape, so the whole call - including the NCCL all-gather of the sharded
+mode - is captured once into a CUDA graph and replayed per frame; only the inputs are copied
+into static buffers.  This removes the Python / launch latency that otherwise bounds small
+per-rank workloads.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import sharding
+
+
+class GraphedDecoder:
+    """decoder: DQDecoder(return_intermediate=True).  Inputs are example tensors whose shapes /
+    dtypes fix the graph; `meta` (cameras) is treated as constant (packed once)."""
+
+    def __init__(self, decoder, tgt, reference_points, src_views: Sequence[torch.Tensor], meta,
+                 spatial_shapes, level_start_index, query_pos, *, threshold: float,
+                 shard: Optional[tuple] = None, num_queries: Optional[int] = None, joints: int = 15,
+                 warmup: int = 2):
+        self.decoder = decoder
+        self.threshold = threshold
+        self.shard = shard
+        self.meta, self.shapes, self.lsi = meta, spatial_shapes, level_start_index
+        self.s_tgt = tgt.clone()
+        self.s_ref = reference_points.clone()
+        self.s_qpos = query_pos.clone()
+        self.s_feats = [s.clone() for s in src_views]
+        self.num_queries, self.joints = num_queries, joints
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.out = self._run()
+
+    def _run(self):
+        if self.shard is not None:
+            rank, world, group = self.shard[:3]
+            return sharding.sharded_decoder_forward(
+                self.decoder, self.s_tgt, self.s_ref, self.s_feats, self.meta, self.shapes, self.lsi,
+                self.s_qpos, threshold=self.threshold, num_queries=self.num_queries,
+                joints=self.joints, rank=rank, world=world, group=group, check=False)
+        hs, refs, refs2d, proj2d, cls = self.decoder(
+            self.s_tgt, self.s_ref, self.s_feats, self.meta, self.shapes, self.lsi, None,
+            query_pos=self.s_qpos, threshold=self.threshold)
+        return refs[-1], cls[-1], hs, refs, refs2d, proj2d, cls
+
+    def __call__(self, tgt=None, reference_points=None, src_views=None, query_pos=None):
+        """Copies the given inputs (device or pinned host tensors) into the static buffers,
+        replays the graph and returns (poses (B,Q*J,3), class prob (B,Q,2), ...)."""
+        if tgt is not None:
+            self.s_tgt.copy_(tgt, non_blocking=True)
+        if reference_points is not None:
+            self.s_ref.copy_(reference_points, non_blocking=True)
+        if query_pos is not None:
+            self.s_qpos.copy_(query_pos, non_blocking=True)
+        if src_views is not None:
+            for d, s in zip(self.s_feats, src_views):
+                d.copy_(s, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+    def empty_scene_layers(self) -> List[int]:
+        """Sharded mode only (host sync): layers in which no rank selected any query - the
+        caller must then fall back to sharding.sharded_decoder_forward(check=True)."""
+        if self.shard is None:
+            return []
+        return (self.out[2] == 0).nonzero().flatten().tolist()

@@ -6,10 +6,12 @@ so contiguous blocks of Q/G queries (all J joints of a query stay together) are 
 given the read-only pyramid and cameras, which every rank holds (the value projection is
 recomputed per rank: 0.2 GB of HBM traffic beats all-gathering it over NVLink).
 
-Exchange steps:
-  * per layer: ONE 4-byte all-reduce of the selected-query count, only to reproduce the
-    reference's global "always one query" rule (dq_decoder.py:620-623) bit-exactly;
-  * at the end: ONE all-gather of the final poses / scores (188 B per query).
+Exchange step: ONE all-gather per decoder call, of the final poses, scores and the per-layer
+selected-query counts (188 B per query + 4 L bytes per rank).  The counts exist only to
+reproduce the reference's GLOBAL "always one query" rule (dq_decoder.py:620-623) bit-exactly
+without a per-layer collective: ranks run all layers assuming some rank selected something;
+if the gathered counts show a layer where nobody did (an empty scene), the call is re-run
+with rank 0 applying the rule in those layers.
 One process per GPU; works with the `nccl` backend on GPUs and `gloo` on CPU tensors (the
 collectives are the only thing this module does - tests/test_sharding_gloo.py).
 """
@@ -36,7 +38,8 @@ def shard_points(t: torch.Tensor, num_queries: int, joints: int, rank: int, worl
 
 def apply_global_min_one(selected: torch.Tensor, info: torch.Tensor, rank: int,
                          group=None) -> torch.Tensor:
-    """selected (B,Ql) uint8 and info[0] = local count (from mvg_select_pad with min_one=0).
+    """Eager variant with one tiny all-reduce (kept for tests / single layers):
+    selected (B,Ql) uint8 and info[0] = local count (from mvg_select_pad with min_one=0).
     If NO rank selected anything, global (frame 0, query 0) - rank 0's local (0,0) - is."""
     total = info[0:1].clone()
     dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
@@ -52,10 +55,70 @@ def allgather_queries(t: torch.Tensor, num_queries: int, per_query: int, world: 
     B = t.shape[0]
     sizes = [shard_bounds(num_queries, r, world) for r in range(world)]
     if len({b - a for a, b in sizes}) == 1:
-        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+        out = torch.empty(world * t.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous().view(-1), group=group)
+        out = out.view((world,) + tuple(t.shape))
         return out.transpose(0, 1).reshape((B, num_queries * per_query) + tuple(t.shape[2:]))
-    bufs = [torch.empty((B, (b - a) * per_query) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device)
-            for a, b in sizes]
-    dist.all_gather(bufs, t.contiguous(), group=group)
-    return torch.cat(bufs, dim=1)
+    # uneven split: pad every shard to the largest one, gather, drop the padding
+    mx = max(b - a for a, b in sizes) * per_query
+    pad = torch.zeros((B, mx) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device)
+    pad[:, :t.shape[1]] = t
+    out = torch.empty(world * pad.numel(), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, pad.view(-1), group=group)
+    out = out.view((world,) + tuple(pad.shape))
+    return torch.cat([out[r, :, :(b - a) * per_query] for r, (a, b) in enumerate(sizes)], dim=1)
+
+
+def gather_results(poses: torch.Tensor, prob: torch.Tensor, counts: torch.Tensor, num_queries: int,
+                   joints: int, world: int, group=None):
+    """One collective: packs (poses (B,Ql*J,3), prob (B,Ql,2), counts (L,)) of every rank into a
+    single fp32 buffer, all-gathers it, and unpacks.  -> poses (B,Q*J,3), prob (B,Q,2),
+    global_counts (L,) = per-layer number of selected queries over all ranks."""
+    B = poses.shape[0]
+    sizes = [shard_bounds(num_queries, r, world) for r in range(world)]
+    ql_max = max(b - a for a, b in sizes)
+    L = counts.numel()
+    n_pose, n_prob = B * ql_max * joints * 3, B * ql_max * 2
+    buf = torch.zeros(n_pose + n_prob + L, dtype=torch.float32, device=poses.device)
+    ql = poses.shape[1] // joints
+    buf[:n_pose].view(B, ql_max * joints, 3)[:, :ql * joints] = poses
+    buf[n_pose:n_pose + n_prob].view(B, ql_max, 2)[:, :ql] = prob
+    buf[n_pose + n_prob:] = counts.to(torch.float32)
+    out = torch.empty(world * buf.numel(), dtype=torch.float32, device=poses.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    out = out.view(world, -1)
+    full_pose = torch.cat([out[r, :n_pose].view(B, ql_max * joints, 3)[:, :(b - a) * joints]
+                           for r, (a, b) in enumerate(sizes)], dim=1)
+    full_prob = torch.cat([out[r, n_pose:n_pose + n_prob].view(B, ql_max, 2)[:, :(b - a)]
+                           for r, (a, b) in enumerate(sizes)], dim=1)
+    global_counts = out[:, n_pose + n_prob:].sum(0)
+    return full_pose, full_prob, global_counts
+
+
+def sharded_decoder_forward(decoder, tgt, reference_points, src_views, meta, spatial_shapes,
+                            level_start_index, query_pos, *, threshold, num_queries, joints, rank,
+                            world, group=None, check: bool = True):
+    """Runs `decoder` (a DQDecoder with return_intermediate=True) on this rank's query block and
+    returns the gathered (poses (B,Q*J,3), class prob (B,Q,2)) of the LAST layer, identical on
+    every rank and bit-identical to the unsharded decoder.  `check=False` skips the (host-
+    synchronising) empty-scene test and returns the global counts as third value instead."""
+    def run(forced):
+        hs, refs, r2d, p2d, cls = decoder(tgt, reference_points, src_views, meta, spatial_shapes,
+                                          level_start_index, None, query_pos=query_pos,
+                                          threshold=threshold, shard=(rank, world, group, forced))
+        return gather_results(refs[-1], cls[-1], decoder.last_shard_counts, num_queries, joints,
+                              world, group)
+    poses, prob, gcounts = run(None)
+    if not check:
+        return poses, prob, gcounts
+    empty = (gcounts == 0).nonzero().flatten().tolist()        # host sync; rare slow path below
+    if empty:
+        # layers after the first empty one see different inputs: iterate until consistent
+        forced = set()
+        while True:
+            forced.add(min(l for l in empty if l not in forced))
+            poses, prob, gcounts = run(forced)
+            empty = [l for l in (gcounts == 0).nonzero().flatten().tolist() if l not in forced]
+            if not empty:
+                break
+    return poses, prob
