@@ -71,7 +71,11 @@ project_sample_kernel(const float* __restrict__ ref3d, const MvgCamera* __restri
   const int ld = prm.ld_vg;
   const uint32_t ld16 = static_cast<uint32_t>(prm.ld_vg) >> 3;   // row stride in 16-byte units
   constexpr int NS = LV * 8;           // samples per head
-  const int m = lane >> 2, sub = lane & 3;
+  // phase-B ownership: head m = lane & 7, sample group sub = lane >> 3 (samples r = sub + 4 i):
+  // a quarter-warp then stores 8 consecutive float4 slots [r][0..7] (conflict-free).
+  // phase-C ownership: head mc = lane >> 2, channel chunk subc = lane & 3.
+  const int m = lane & 7, sub = lane >> 3;
+  const int mc = lane >> 2, subc = lane & 3;
 
   // Each CTA owns one contiguous range of (b, v, n) items; its 16 warps walk it together
   // (warp w: first + w, first + w + 16, ...), so at any moment one SM works on ~one person's
@@ -134,6 +138,12 @@ project_sample_kernel(const float* __restrict__ ref3d, const MvgCamera* __restri
         }
       }
 
+      float inv_w[LV], inv_h[LV];
+#pragma unroll
+      for (int l = 0; l < LV; ++l) {
+        inv_w[l] = 1.f / static_cast<float>(prm.level_w[l]);
+        inv_h[l] = 1.f / static_cast<float>(prm.level_h[l]);
+      }
       // ---------------- phase A (a4 i+iii): sample the pre-projected map G at the reference point
       if (lane < kQP / 8) {
         const float* qp = qproj + (static_cast<int64_t>(b) * N + n) * kQP + lane * 8;
@@ -195,29 +205,32 @@ project_sample_kernel(const float* __restrict__ ref3d, const MvgCamera* __restri
           lg[i] = sc.proj[g >> 6][128 + (g & 63)];
           mx = fmaxf(mx, lg[i]);
         }
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < NS / 4; ++i) {
           lg[i] = expf(lg[i] - mx);
           sum += lg[i];
         }
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+        const float inv_sum = 1.f / sum;
 #pragma unroll
         for (int i = 0; i < NS / 4; ++i) {
           const int r = sub + 4 * i;
           const int l = i >> 1;                        // == r >> 3 because sub < 4 (static index)
-          const float wgt = lg[i] / sum;
+          const float wgt = lg[i] * inv_sum;
           const int f = m * (NS * 2) + 2 * r;          // flat offset index after the `.view`
           const float2 off = *reinterpret_cast<const float2*>(&sc.proj[f >> 7][f & 127]);
           const int W = prm.level_w[l], H = prm.level_h[l], start = prm.level_start[l];
           const float rlx = refl_x[l], rly = refl_y[l];
           const float fW = static_cast<float>(W), fH = static_cast<float>(H);
           // projattn.py:186-191, then deform_im2col_cuda.cuh:291-301 and :41-93
-          const float loc_x = fadd(rlx, fdiv(off.x, fW));
-          const float loc_y = fadd(rly, fdiv(off.y, fH));
+          // (reciprocal instead of the reference's division: the offsets come from the bf16 map,
+          //  so this path is not bit-comparable anyway; mvg_deform_forward keeps exact inputs)
+          const float loc_x = fadd(rlx, fmul(off.x, inv_w[l]));
+          const float loc_y = fadd(rly, fmul(off.y, inv_h[l]));
           const float h_im = fsub(fmul(loc_y, fH), 0.5f);
           const float w_im = fsub(fmul(loc_x, fW), 0.5f);
           const bool inside = h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW;
@@ -246,15 +259,15 @@ project_sample_kernel(const float* __restrict__ ref3d, const MvgCamera* __restri
 
       // ---------------- phase C (a5): gather 4 corners x NS samples, 8 channels per lane
       uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};     // 8 fp32 accumulators as 4 packed pairs
-      const uint4* vlane16 = reinterpret_cast<const uint4*>(vrow + m * 32 + sub * 8);
+      const uint4* vlane16 = reinterpret_cast<const uint4*>(vrow + mc * 32 + subc * 8);
 #pragma unroll
       for (int l = 0; l < LV; ++l) {
         const uint32_t rowstep16 = static_cast<uint32_t>(prm.level_w[l]) * ld16;
 #pragma unroll 4
         for (int p = 0; p < 8; ++p) {
           const int r = l * 8 + p;
-          const float4 cwv = sc.cw[r * kHeads + m];
-          const uint32_t bs = static_cast<uint32_t>(sc.base[r * kHeads + m]);
+          const float4 cwv = sc.cw[r * kHeads + mc];
+          const uint32_t bs = static_cast<uint32_t>(sc.base[r * kHeads + mc]);
           const uint32_t o00 = bs >> 2;
           const uint32_t o01 = o00 + ((bs & 1u) ? ld16 : 0u);
           const uint32_t o10 = o00 + ((bs & 2u) ? rowstep16 : 0u);
