@@ -304,34 +304,92 @@ def run_ours(a):
     prof_steps = n_prof
     value = B * Q * a.steps / (total_ms * 1e-3)
 
-    # ---- end to end: pinned host buffers in, poses + scores out, every step
+    # ---- end to end: pinned host buffers in, poses + scores out, every step.
+    # Two-deep software pipeline (what a serving loop does): while frame i runs on the compute
+    # stream, frame i+1's inputs are uploaded on a copy stream into the second graph's static
+    # buffers; every frame's inputs cross PCIe and every frame's result is read back on the host.
     e2e = None
     if not a.no_e2e:
         h2d = sum(t.numel() * t.element_size() for t in list(host.values()) + host_feats)
-        out_pose = torch.empty((B, Q * J, 3), dtype=torch.float32).pin_memory()
-        out_prob = torch.empty((B, Q, 2), dtype=torch.float32).pin_memory()
+        n_buf = 2 if graphed is not None else 1
+        out_pose = [torch.empty((B, Q * J, 3), dtype=torch.float32).pin_memory() for _ in range(n_buf)]
+        out_prob = [torch.empty((B, Q, 2), dtype=torch.float32).pin_memory() for _ in range(n_buf)]
+        if graphed is not None:
+            from mvgformer_b200.graphs import GraphedDecoder
+            g2 = GraphedDecoder(dec, d["tgt"], d["reference_points"], feats, meta, shapes, lsi,
+                                d["query_pos"], threshold=a.threshold,
+                                shard=(rank, world, None) if world > 1 else None, num_queries=Q, joints=J)
+            graphs = [graphed, g2]
+            copy_stream = torch.cuda.Stream()
+            h2d_done = [torch.cuda.Event() for _ in range(2)]
+            compute_done = [torch.cuda.Event() for _ in range(2)]
+            d2h_done = [torch.cuda.Event() for _ in range(2)]
+            state = {"step": 0}
+            checksum = {"v": 0.0}
 
-        def e2e_step():
-            if graphed is not None:      # H2D into the graph's static inputs, replay, D2H
-                out = graphed(host["tgt"], host["reference_points"], host_feats, host["query_pos"])
-                poses, prob = out[0], out[1]
-            else:
+            def e2e_step():
+                s_ = state["step"]
+                b_ = s_ & 1
+                main = torch.cuda.current_stream()
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(compute_done[b_])      # buffers of frame s-2 are free
+                    graphs[b_].load_inputs(host["tgt"], host["reference_points"], host_feats, host["query_pos"])
+                    h2d_done[b_].record(copy_stream)
+                main.wait_event(h2d_done[b_])
+                out = graphs[b_].replay()
+                out_pose[b_].copy_(out[0], non_blocking=True)
+                out_prob[b_].copy_(out[1], non_blocking=True)
+                compute_done[b_].record(main)
+                d2h_done[b_].record(main)
+                if s_ > 0:                                        # consume frame s-1 on the host
+                    d2h_done[b_ ^ 1].synchronize()
+                    checksum["v"] += float(out_prob[b_ ^ 1][0, 0, 1])
+                state["step"] = s_ + 1
+
+            def e2e_drain():
+                torch.cuda.synchronize()
+                checksum["v"] += float(out_prob[(state["step"] - 1) & 1][0, 0, 1])
+        else:
+            def e2e_step():
                 inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
                 fts = [s.to(dev, non_blocking=True) for s in host_feats]
                 poses, prob = forward(inp, fts, check=True)   # result consumed on the host
-            out_pose.copy_(poses, non_blocking=True)
-            out_prob.copy_(prob, non_blocking=True)
-            torch.cuda.current_stream().synchronize()     # the caller consumes the result
-            if graphed is not None and world > 1 and graphed.empty_scene_layers():
-                forward(d, feats, check=True)             # exact slow path (never on this data)
+                out_pose[0].copy_(poses, non_blocking=True)
+                out_prob[0].copy_(prob, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+            def e2e_drain():
+                pass
 
         for _ in range(3):
             e2e_step()
-        e2e_ms = timed(e2e_step, a.steps)
+        e2e_drain()
+
+        def e2e_all():
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        for _ in range(a.steps):
+            e2e_step()
+        e2e_drain()                                               # last frame's result on the host
+        e_ev.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms_t = torch.tensor([max(s_ev.elapsed_time(e_ev), wall_ms)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        barrier()
+        e2e_ms = float(ms_t.item())
+        if graphed is not None and world > 1 and (graphs[0].empty_scene_layers() or graphs[1].empty_scene_layers()):
+            raise SystemExit("bench: empty-scene slow path hit on synthetic data (unexpected)")
         e2e = {"value": B * Q * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(out_pose.numel() * 4 + out_prob.numel() * 4),
-               "ms_per_step": e2e_ms / a.steps}
+               "d2h_bytes_per_step": int(out_pose[0].numel() * 4 + out_prob[0].numel() * 4),
+               "ms_per_step": e2e_ms / a.steps,
+               "pipeline": "2-deep: H2D of frame i+1 overlaps compute of frame i" if graphed is not None
+               else "none (eager)"}
 
     # ---- roofline of the dominant kernel (fused projection + sampling), live CUDA events
     n_pts = ql * J

@@ -70,6 +70,18 @@ class GraphedDecoder:
         self.graph.replay()
         return self.out
 
+    def load_inputs(self, tgt, reference_points, src_views, query_pos) -> None:
+        """Enqueues the H2D / D2D copies of one frame's inputs on the CURRENT stream."""
+        self.s_tgt.copy_(tgt, non_blocking=True)
+        self.s_ref.copy_(reference_points, non_blocking=True)
+        self.s_qpos.copy_(query_pos, non_blocking=True)
+        for d, s in zip(self.s_feats, src_views):
+            d.copy_(s, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
     def empty_scene_layers(self) -> List[int]:
         """Sharded mode only (host sync): layers in which no rank selected any query - the
         caller must then fall back to sharding.sharded_decoder_forward(check=True)."""
