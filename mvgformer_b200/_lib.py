@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmvg_b200.so")
+LIB_PATH = os.environ.get("MVG_LIB_PATH", os.path.join(_HERE, "libmvg_b200.so"))   # override: A/B experiments
 
 MVG_F32, MVG_BF16 = 0, 1
 MVG_MAX_LEVELS = 4

@@ -21,7 +21,14 @@
 
 namespace mvg {
 
-constexpr int kWarps = 16;         // warps per CTA; one persistent CTA per SM
+#ifndef MVG_PS_WARPS
+#define MVG_PS_WARPS 16
+#endif
+#ifndef MVG_PS_UNROLL
+#define MVG_PS_UNROLL 4
+#endif
+constexpr int kWarps = MVG_PS_WARPS;   // warps per CTA; one persistent CTA per SM
+constexpr int kPsUnroll = MVG_PS_UNROLL;
 constexpr int kQP = 192;           // 128 offset channels + 64 logit channels per level
 constexpr int kHeads = 8;
 constexpr int kVgValueCols = 256;  // value columns precede the G columns in a vg row
@@ -263,7 +270,7 @@ project_sample_kernel(const float* __restrict__ ref3d, const MvgCamera* __restri
 #pragma unroll
       for (int l = 0; l < LV; ++l) {
         const uint32_t rowstep16 = static_cast<uint32_t>(prm.level_w[l]) * ld16;
-#pragma unroll 4
+#pragma unroll kPsUnroll
         for (int p = 0; p < 8; ++p) {
           const int r = l * 8 + p;
           const float4 cwv = sc.cw[r * kHeads + mc];
