@@ -199,6 +199,9 @@ MVG_API int mvg_add_layernorm(const float* a, const void* b, int b_dtype, const 
                       void* out_bf16, void* stream);
 MVG_API int mvg_class_prob(const float* cls, int batch, int queries, int joints, float* prob,
                    void* stream);
+/* out_bf16[i] = bf16(a[i] + b[i]) (b may be NULL): `with_pos_embed` + operand cast,
+ * dq_decoder.py:580 / mvp_decoder.py:90-92.  n % 8 == 0. */
+MVG_API int mvg_add_cast_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream);
 /* class_embed Linear(256,2) + sigmoid + mean over joints in one pass (fp32):
  * x (B, Q*J, 256) fp32, w (2,256), bias (2) -> prob (B,Q,2). */
 MVG_API int mvg_class_head(const float* x, const float* w, const float* bias, int batch, int queries,

@@ -52,6 +52,7 @@ SIGNATURES = {
     "mvg_masked_view_mean": [_P, _P, _I, _I, _I, _I, _P, _P],
     "mvg_add_layernorm": [_P, _P, _I, _P, _P, _L, _I, _F, _P, _P, _P],
     "mvg_class_prob": [_P, _I, _I, _I, _P, _P],
+    "mvg_add_cast_bf16": [_P, _P, _P, _L, _P],
     "mvg_class_head": [_P, _P, _P, _I, _I, _I, _P, _P],
 }
 

@@ -150,7 +150,73 @@ class_head_kernel(const float* __restrict__ x, const float* __restrict__ w,
   }
 }
 
+// out_bf16 = bf16(a + b)   (with_pos_embed + cast for the tensor-core operand, dq_decoder.py:580)
+__global__ void __launch_bounds__(256)
+add_cast_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n8,
+                     __nv_bfloat16* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(a) + 2 * i);
+  const float4 a1 = __ldg(reinterpret_cast<const float4*>(a) + 2 * i + 1);
+  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+  if (b != nullptr) {
+    b0 = __ldg(reinterpret_cast<const float4*>(b) + 2 * i);
+    b1 = __ldg(reinterpret_cast<const float4*>(b) + 2 * i + 1);
+  }
+  uint4 o;
+  o.x = pack_bf16x2(a0.x + b0.x, a0.y + b0.y); o.y = pack_bf16x2(a0.z + b0.z, a0.w + b0.w);
+  o.z = pack_bf16x2(a1.x + b1.x, a1.y + b1.y); o.w = pack_bf16x2(a1.z + b1.z, a1.w + b1.w);
+  reinterpret_cast<uint4*>(out)[i] = o;
+}
+
+// class head, one CTA per (b, q), one warp per joint: dot products by warp shuffle, the mean over
+// joints through shared memory.
+__global__ void __launch_bounds__(512)
+class_head_kernel_v2(const float* __restrict__ x, const float* __restrict__ w,
+                     const float* __restrict__ bias, int J, float* __restrict__ prob) {
+  __shared__ float part[16][2];
+  const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int64_t bq = blockIdx.x;
+  if (j < J) {
+    const float* row = x + (bq * J + j) * 256 + lane * 8;
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(row));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(row + 4));
+    const float4 w00 = __ldg(reinterpret_cast<const float4*>(w + lane * 8));
+    const float4 w01 = __ldg(reinterpret_cast<const float4*>(w + lane * 8 + 4));
+    const float4 w10 = __ldg(reinterpret_cast<const float4*>(w + 256 + lane * 8));
+    const float4 w11 = __ldg(reinterpret_cast<const float4*>(w + 256 + lane * 8 + 4));
+    float d0 = a0.x * w00.x + a0.y * w00.y + a0.z * w00.z + a0.w * w00.w + a1.x * w01.x + a1.y * w01.y +
+               a1.z * w01.z + a1.w * w01.w;
+    float d1 = a0.x * w10.x + a0.y * w10.y + a0.z * w10.z + a0.w * w10.w + a1.x * w11.x + a1.y * w11.y +
+               a1.z * w11.z + a1.w * w11.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+    }
+    if (lane == 0) {
+      part[j][0] = 1.f / (1.f + expf(-(d0 + __ldg(bias))));
+      part[j][1] = 1.f / (1.f + expf(-(d1 + __ldg(bias + 1))));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float s = 0.f;
+    for (int k = 0; k < J; ++k) s += part[k][threadIdx.x];
+    prob[bq * 2 + threadIdx.x] = s / static_cast<float>(J);
+  }
+}
+
 }  // namespace mvg
+
+extern "C" int mvg_add_cast_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream) {
+  using namespace mvg;
+  MVG_REQUIRE(a && out_bf16 && n > 0 && n % 8 == 0, "mvg_add_cast_bf16: bad argument (n must be a multiple of 8)");
+  const int64_t n8 = n / 8;
+  add_cast_bf16_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, b, n8, static_cast<__nv_bfloat16*>(out_bf16));
+  return check_launch("mvg_add_cast_bf16");
+}
 
 extern "C" int mvg_class_head(const float* x, const float* w, const float* bias, int batch,
                               int queries, int joints, float* prob, void* stream) {
@@ -158,8 +224,12 @@ extern "C" int mvg_class_head(const float* x, const float* w, const float* bias,
   MVG_REQUIRE(x && w && bias && prob && batch > 0 && queries > 0 && joints > 0,
               "mvg_class_head: bad argument");
   const int64_t bq = static_cast<int64_t>(batch) * queries;
-  class_head_kernel<<<static_cast<unsigned>((bq + 7) / 8), 256, 0,
-                      static_cast<cudaStream_t>(stream)>>>(x, w, bias, bq, joints, prob);
+  if (joints <= 16)
+    class_head_kernel_v2<<<static_cast<unsigned>(bq), joints * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, w, bias, joints, prob);
+  else
+    class_head_kernel<<<static_cast<unsigned>((bq + 7) / 8), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(x, w, bias, bq, joints, prob);
   return check_launch("mvg_class_head");
 }
 

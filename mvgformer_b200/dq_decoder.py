@@ -214,7 +214,8 @@ class DQDecoderLayer(nn.Module):
         tgt = tgt.float().contiguous()
         # 2. per-point part of the offset / logit projections
         with prof.stage("qproj"):
-            q_bf = (tgt if query_pos is None else tgt + query_pos).to(torch.bfloat16)
+            qp = None if query_pos is None else query_pos.float().contiguous()
+            q_bf = ops.add_cast_bf16(tgt, qp)                                    # with_pos_embed
             qproj = linear(q_bf, pw["w_q"], pw["b_q"], out_dtype=torch.float32)  # (B,N,192)
         # 3. fused projection + sampling
         vg = ctx.vg_for(self)

@@ -175,3 +175,12 @@ def class_head(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, queries: in
     check(lib.mvg_class_head(x.data_ptr(), w.data_ptr(), bias.data_ptr(), B, queries, joints,
                              prob.data_ptr(), stream_ptr(x.device)), "mvg_class_head")
     return prob
+
+
+def add_cast_bf16(a: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+    """bf16(a + b) in one pass; a, b fp32 contiguous, numel % 8 == 0."""
+    lib = _lib.load()
+    out = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    check(lib.mvg_add_cast_bf16(a.data_ptr(), _lib.ptr(b), out.data_ptr(), a.numel(),
+                                stream_ptr(a.device)), "mvg_add_cast_bf16")
+    return out
