@@ -411,7 +411,7 @@ def run_ours(a):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("project_sample_fused_dram_bytes_per_launch")
-    roofline = {"kernel": "mvg::project_sample_kernel<3>", "bound": "hbm", "achieved": achieved,
+    roofline = {"kernel": "mvg::gather_kernel<3> (+ project_compact_kernel)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "algorithmic_bytes_per_launch": int(alg_bytes),
                 "launch_ms": st["mean_ms"], "launches_timed": st["count"], "peak_source": peak_src,

@@ -126,7 +126,11 @@ MVG_API int mvg_linear_bf16(const void* A, const void* W, const float* bias, voi
  *   network-image coordinates, bounding (B,V,N) uint8.
  * ProjAttn.forward entry (projattn.py:115): when `refl_in` (B,V,N,Lv,2) is non-NULL the
  *   projection is skipped and the per-level normalised reference points are read from it
- *   (ref3d, cams, ref2d, bounding may then be NULL).
+ *   (ref3d, cams, ref2d, bounding, workspace may then be NULL).
+ * Out-of-view points (bounding == 0): the reference multiplies their attention feature by 0
+ *   (dq_decoder.py:585-586) and reads it nowhere else, so they are not gathered; their
+ *   `sampled` rows are zeros.  `workspace` (device, 4 * (B*V*N + 4) bytes, contents
+ *   irrelevant on entry) receives the count and the list of in-view items.
  */
 typedef struct {
   int batch, views, points;     /* B, V, N */
@@ -142,7 +146,7 @@ typedef struct {
 MVG_API int mvg_project_sample_fused(const float* ref3d, const float* cams, const void* vg,
                              const float* qproj, const MvgSampleParams* prm, void* sampled,
                              float* ref2d, uint8_t* bounding, const float* refl_in,
-                             void* stream);
+                             void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Integer path of the query filter (dq_decoder.py:596-656): threshold mask, torch.where

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("MVG_LIB_PATH", os.path.join(_HERE, "libmvg_b200.so"))
 MVG_F32, MVG_BF16 = 0, 1
 MVG_MAX_LEVELS = 4
 MVG_CAM_FLOATS = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class MvgError(RuntimeError):
@@ -45,7 +45,7 @@ SIGNATURES = {
     "mvg_deform_backward": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "mvg_pyramid_to_channels_last": [_P, _I, _I, _P, _I, _I, _P, _P],
     "mvg_linear_bf16": [_P, _P, _P, _P, _I, _L, _I, _I, _L, _I, _P, _P],
-    "mvg_project_sample_fused": [_P, _P, _P, _P, C.POINTER(MvgSampleParams), _P, _P, _P, _P, _P],
+    "mvg_project_sample_fused": [_P, _P, _P, _P, C.POINTER(MvgSampleParams), _P, _P, _P, _P, _P, _P],
     "mvg_select_pad": [_P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "mvg_offsets_dlt": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P],
     "mvg_triangulate": [_P, _P, _P, _I, _I, _I, _P, _P],
