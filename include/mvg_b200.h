@@ -211,6 +211,42 @@ MVG_API int mvg_add_cast_bf16(const float* a, const float* b, void* out_bf16, in
 MVG_API int mvg_class_head(const float* x, const float* w, const float* bias, int batch, int queries,
                    int joints, float* prob, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * The steps either side of the decoder.
+ *
+ * mvg_init_queries: query / reference-point construction of DyanmicQueryTransformer.forward
+ *   (lib/models/dq_transformer.py:394-432 query_embed_type='person_joint'; :298-323
+ *   init_ref_method='sample_space'; norm2absolute multi_view_pose_transformer.py:575-580).
+ *   joint_emb (J,2C), inst_emb (Q,2C) fp32; lin (grid_n) fp32 = torch.linspace(0,1,grid_n),
+ *   grid_n = ceil(sqrt(Q)); tpose (J,3) float64 mm; space_size / space_center: 3 HOST floats.
+ *   Outputs: query_pos, tgt (B,Q*J,C) fp32 (first / second half of the summed embeddings),
+ *   ref (B,Q*J,3) fp32 mm.
+ *
+ * mvg_assemble_predictions: poses (B,Q*J,3), prob (B,Q,2) = last layer's class output ->
+ *   pred (B,Q,J,5) = [x, y, z, (score > thr) - 1, score], score = sigmoid(inverse_sigmoid(prob[...,1]))
+ *   (dq_transformer.py:568, util/misc.py:608-612, lib/core/function.py:386-392), plus the score
+ *   filter of run/validate_3d.py:229: valid_ids (B,Q) int32 = query ids with score > thr in
+ *   ascending order (first valid_count[b] entries valid), valid_count (B) int32.
+ *
+ * mvg_nearby_joints_nms: lib/core/nms.py:210-284 (combined_input=True, max_dets=-1) on the valid
+ *   poses of every frame.  workspace: B * Q * ceil(Q/32) uint32 (close-instance bit matrix).
+ *   keep_compact (B,Q) int32 = kept indices INTO THE FILTERED ARRAY in the order the reference
+ *   appends them (its return value), keep_query (B,Q) = the same as query ids, keep_count (B).
+ *   Q <= 4096, J <= 32.  Equal scores: the reference's argsort is not stable (order
+ *   unspecified); here the larger index goes first.
+ */
+MVG_API int mvg_init_queries(const float* joint_emb, const float* inst_emb, const float* lin,
+                     const double* tpose, const float* space_size, const float* space_center,
+                     int batch, int queries, int joints, int channels, int grid_n,
+                     float* query_pos, float* tgt, float* ref, void* stream);
+MVG_API int mvg_assemble_predictions(const float* poses, const float* prob, int batch, int queries,
+                             int joints, float threshold, float* pred, int32_t* valid_ids,
+                             int32_t* valid_count, void* stream);
+MVG_API int mvg_nearby_joints_nms(const float* pred, const int32_t* valid_ids, const int32_t* valid_count,
+                          int batch, int queries, int joints, float dist_thr,
+                          int num_nearby_joints_thr, uint32_t* workspace, int32_t* keep_compact,
+                          int32_t* keep_query, int32_t* keep_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,7 +2,10 @@
 
 Host-side mirror of the reference's operator / module interface for ONE hot path
 (SURVEY.md section 8): `Deformable.deform_forward/backward`, `DeformFunction`, `ProjAttn`,
-`DQDecoderLayer`, `DQDecoder`, `multiview.triangulate_batch_of_points_batch_version`.
+`DQDecoderLayer`, `DQDecoder`, `multiview.triangulate_batch_of_points_batch_version`, and the
+steps either side of the decoder (section 8f): `QueryInit` (query / reference-point construction
+of `DyanmicQueryTransformer.forward`) and `postprocess` (prediction assembly + score filter +
+`nearby_joints_nms` of the validation loop).
 All arithmetic runs in hand-written CUDA behind the C ABI of include/mvg_b200.h.
 """
 from . import _lib  # noqa: F401
@@ -11,6 +14,9 @@ from .deform_func import DeformFunction  # noqa: F401
 from .projattn import ProjAttn  # noqa: F401
 from .dq_decoder import DQDecoder, DQDecoderLayer, MLP, offset_net  # noqa: F401
 from . import multiview  # noqa: F401
+from .query_init import QueryInit  # noqa: F401
+from . import postprocess  # noqa: F401
 
 __all__ = ["deform_forward", "deform_backward", "install_as_Deformable", "DeformFunction",
-           "ProjAttn", "DQDecoder", "DQDecoderLayer", "MLP", "offset_net", "multiview"]
+           "ProjAttn", "DQDecoder", "DQDecoderLayer", "MLP", "offset_net", "multiview", "QueryInit",
+           "postprocess"]

@@ -22,15 +22,24 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 import torch
 
-# reference `tpose.pt` (float64, (15,3), mm) - data, printed from the reference root
+# reference `tpose.pt` (float64, (15,3), mm) - data, printed from the reference root with
+# full float64 precision (oracle/gen_golden.py asserts bit-equality with the file)
 TPOSE_MM = np.array([
-    [-8.0720, -32.5520, 571.1680], [60.7220, 149.9020, 738.6780], [0.0, 0.0, 0.0],
-    [-164.4850, 40.3180, 565.1980], [-240.8650, 30.6990, 320.6780],
-    [-50.1000, 157.6670, 396.0380], [-84.9300, 59.3810, -4.9090],
-    [-85.8840, 12.7500, -397.5280], [-74.3460, -30.8230, -712.4110],
-    [143.1300, -101.2810, 584.0480], [249.9620, -103.4240, 364.7480],
-    [192.5020, 82.1720, 451.7580], [84.9310, -59.3810, 4.9090],
-    [142.1820, -112.1650, -360.1260], [177.2020, -227.3750, -712.7630]], dtype=np.float64)
+    [-8.072000000000116, -32.55199999999991, 571.168],
+    [60.721999999999866, 149.90200000000004, 738.678],
+    [0.0, 0.0, 0.0],
+    [-164.48500000000013, 40.317999999999984, 565.1979999999998],
+    [-240.865, 30.698999999999955, 320.678],
+    [-50.100000000000136, 157.66700000000003, 396.0380000000001],
+    [-84.93000000000018, 59.38099999999997, -4.908999999999992],
+    [-85.88400000000013, 12.75, -397.528],
+    [-74.34600000000012, -30.82299999999998, -712.4110000000001],
+    [143.12999999999988, -101.28099999999995, 584.0480000000001],
+    [249.96199999999988, -103.42399999999998, 364.74799999999993],
+    [192.50199999999984, 82.17200000000003, 451.7579999999999],
+    [84.93099999999993, -59.38099999999997, 4.908999999999992],
+    [142.1819999999999, -112.16499999999996, -360.12600000000003],
+    [177.20199999999988, -227.375, -712.763]], dtype=np.float64)
 
 PANOPTIC = dict(orig_size=(1920, 1080), net_size=(960, 512),
                 levels=((128, 240), (64, 120), (32, 60)),

@@ -17,6 +17,8 @@ Fixtures (all produced by reference code, file:line given per entry):
   triangulate.npz     multiview.triangulate_batch_of_points_batch_version
                       (lib/mvn/utils/multiview.py:257-269), fp32 (as shipped) and the same
                       reference code fed float64 inputs (its exact-arithmetic answer)
+  pre_post.npz        sample_space reference points (lib/models/dq_transformer.py:298-323),
+                      nearby_joints_nms keep lists (lib/core/nms.py:210-284), inverse_sigmoid
   state_dict_keys.json  parameter names/shapes of the reference DQDecoder
 """
 from __future__ import annotations
@@ -178,6 +180,69 @@ def gen_triangulate():
     np.savez_compressed(os.path.join(GOLD, "triangulate.npz"), **out)
 
 
+def make_pose_sets(seed: int, n: int, dup_frac: float = 0.5):
+    """Synthetic detections for the NMS fixture: clusters of near-duplicate T-poses (what
+    neighbouring queries that converge on the same person look like) + isolated ones.
+    Returns pred (n, 15, 5) float32 = [xyz, 0, score] with distinct scores."""
+    rng = np.random.default_rng(seed)
+    n_people = max(1, int(n * (1 - dup_frac)))
+    roots = rng.uniform([-3500, -4000, 600], [3500, 3000, 1000], size=(n_people, 3))
+    owner = np.concatenate([np.arange(n_people), rng.integers(0, n_people, size=n - n_people)])
+    jitter = rng.normal(0, 1, size=(n, 15, 3)) * rng.choice([5.0, 40.0, 150.0, 400.0], size=(n, 1, 1))
+    kp = roots[owner][:, None, :] + syn.TPOSE_MM[None] + jitter
+    score = rng.permutation(n).astype(np.float64) / n * 0.8 + 0.15 + rng.uniform(0, 1e-4, size=n)
+    pred = np.zeros((n, 15, 5), dtype=np.float32)
+    pred[..., :3] = kp
+    pred[..., 4] = score[:, None]
+    return pred
+
+
+def gen_pre_post():
+    """tests/golden/pre_post.npz:
+      ref_q*      DyanmicQueryTransformer.initialize_reference_points(method='sample_space')
+                  (lib/models/dq_transformer.py:250-323) called unbound on a stand-in `self`
+                  that carries the attributes it reads (norm2absolute, generate_T_pose,
+                  grid_size / grid_center, t_pose_origin = the reference's tpose.pt)
+      nms_keep_*  lib/core/nms.py:210 nearby_joints_nms(pred, 0.3, 7) on seeded pose sets
+      invsig      lib/models/util/misc.py:608 inverse_sigmoid
+    """
+    import importlib
+    import types
+    load_reference()
+    dqt = importlib.import_module("lib.models.dq_transformer")
+    nms = importlib.import_module("lib.core.nms")
+    misc = importlib.import_module("lib.models.util.misc")
+    cls = dqt.DyanmicQueryTransformer
+    tpose = torch.load(os.path.join(os.environ.get("MVG_REFERENCE_ROOT", "/root/reference"), "tpose.pt"),
+                       map_location="cpu")
+    assert np.array_equal(tpose.numpy(), syn.TPOSE_MM), "synthetic.TPOSE_MM drifted from tpose.pt"
+    out = {"tpose": tpose.numpy()}
+    for cfg_name, cfg in (("panoptic", syn.PANOPTIC), ("shelf", syn.SHELF)):
+        for q in (1024, 500, 7):
+            me = types.SimpleNamespace(grid_size=torch.tensor(cfg["space_size"]),
+                                       grid_center=torch.tensor(cfg["space_center"]),
+                                       t_pose_origin=tpose, num_joints=15)
+            me.norm2absolute = types.MethodType(cls.norm2absolute, me)
+            me.generate_T_pose = types.MethodType(cls.generate_T_pose, me)
+            B = 2
+            meta = [{"num_person": torch.zeros(B, dtype=torch.int64),
+                     "joints_3d": torch.zeros(B, 1, 15, 3),
+                     "joints_3d_voxelpose_pred": torch.zeros(B, 1, 15, 5)}]
+            tgt = torch.zeros(B, q * 15, 1)      # only its shape is read (query_num = shape[1] // 15)
+            with torch.no_grad():
+                ref = cls.initialize_reference_points(me, tgt, meta, method="sample_space", value=0)
+            assert ref.shape == (B, q * 15, 3) and ref.dtype == torch.float32
+            out[f"ref_{cfg_name}_q{q}"] = ref.numpy()
+    for seed, n in ((1, 1), (2, 9), (3, 64), (4, 300), (5, 1024)):
+        pred = make_pose_sets(seed, n)
+        keep = nms.nearby_joints_nms(pred, 0.3, 7)
+        out[f"nms_keep_s{seed}"] = np.asarray(keep, dtype=np.int64)
+        out[f"nms_sum_s{seed}"] = np.asarray([checksum(pred)])
+    x = torch.from_numpy(np.random.default_rng(9).uniform(-0.1, 1.1, size=(64,)).astype(np.float32))
+    out["invsig_in"], out["invsig"] = x.numpy(), misc.inverse_sigmoid(x).numpy()
+    np.savez_compressed(os.path.join(GOLD, "pre_post.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)            # deterministic reduction order in the CPU kernels
@@ -186,6 +251,7 @@ def main():
     gen_deform_core()
     gen_project_ref()
     gen_triangulate()
+    gen_pre_post()
     for fn in sorted(os.listdir(GOLD)):
         print(fn, os.path.getsize(os.path.join(GOLD, fn)))
 

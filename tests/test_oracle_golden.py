@@ -189,3 +189,46 @@ def test_state_dict_keys_match_reference(golden_dir):
     dec = mvg.DQDecoder(cfg, layer, SMALL["num_layers"], True)
     mine = {k: list(v.shape) for k, v in dec.state_dict().items()}
     assert mine == ref_keys
+
+
+# ----------------------------------------------------------------------------- section 8f rows 1-2
+def test_pre_post_oracle_matches_reference_golden():
+    """oracle/pre_post_oracle.py vs tests/golden/pre_post.npz (reference functions called as they
+    stand by oracle/gen_golden.py::gen_pre_post): bit-exact reference points, NMS keep lists and
+    inverse_sigmoid."""
+    from oracle import pre_post_oracle as pp
+    from oracle.gen_golden import make_pose_sets, checksum as gsum
+    g = load_golden("pre_post.npz")
+    assert np.array_equal(g["tpose"], syn.TPOSE_MM)
+    tp = torch.from_numpy(syn.TPOSE_MM)
+    for name, cfg in (("panoptic", syn.PANOPTIC), ("shelf", syn.SHELF)):
+        for q in (1024, 500, 7):
+            r = pp.sample_space_reference_points(2, q, cfg["space_size"], cfg["space_center"], tp)
+            assert np.array_equal(r.numpy(), g[f"ref_{name}_q{q}"]), (name, q)
+    # the synthetic scenes use the same construction
+    assert torch.equal(syn.make_reference_points(2, 500, syn.PANOPTIC["space_size"], syn.PANOPTIC["space_center"]),
+                       torch.from_numpy(g["ref_panoptic_q500"]))
+    for seed, n in ((1, 1), (2, 9), (3, 64), (4, 300), (5, 1024)):
+        pred = make_pose_sets(seed, n)
+        assert gsum(pred) == str(g[f"nms_sum_s{seed}"][0])
+        keep = pp.nearby_joints_nms(pred, 0.3, 7)
+        assert np.array_equal(np.asarray(keep, dtype=np.int64), g[f"nms_keep_s{seed}"]), seed
+        assert 0 < len(keep) <= n
+    assert pp.nearby_joints_nms(np.zeros((0, 15, 5), np.float32)) == []
+    x = torch.from_numpy(g["invsig_in"])
+    assert np.array_equal(pp.inverse_sigmoid(x).numpy(), g["invsig"])
+
+
+def test_assemble_predictions_semantics():
+    from oracle import pre_post_oracle as pp
+    rng = np.random.default_rng(3)
+    poses = torch.from_numpy(rng.standard_normal((2, 6 * 15, 3), dtype=np.float32))
+    prob = torch.from_numpy(rng.uniform(0, 1, size=(2, 6, 2)).astype(np.float32))
+    pred = pp.assemble_predictions(poses, prob, 0.3)
+    assert pred.shape == (2, 6, 15, 5)
+    assert torch.equal(pred[..., :3].reshape(2, 90, 3), poses)
+    assert torch.allclose(pred[..., 4], prob[..., 1:2].expand(-1, -1, 15), atol=1e-6)
+    assert torch.equal(pred[..., 3], (pred[..., 4] > 0.3).float() - 1)
+    _, kept = pp.postprocess(poses, prob, 0.3)
+    for b in range(2):
+        assert set(kept[b].tolist()) <= set(np.nonzero(pred[b, :, 0, 3].numpy() >= 0)[0].tolist())
