@@ -301,6 +301,7 @@ def run_ours(a):
     launches_per_step = (_lib.launch_count() - n0) // n_prof
     prof.enable(False)
     stages = prof.summary()
+    inview = prof.notes().get("inview_items", [])
     prof_steps = n_prof
     value = B * Q * a.steps / (total_ms * 1e-3)
 
@@ -411,11 +412,56 @@ def run_ours(a):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("project_sample_fused_dram_bytes_per_launch")
+    # secondary view: what actually bounds the kernel is the L1 data path (profiles/
+    # gather_experiments_r1.md): every in-view item pulls 768 (texel, head) rows of 64 B through
+    # LDG plus 36 x 384 B of the offset/logit map; a warp-level LDG.128 delivers at most 64 B/clk/SM.
+    l1 = None
+    if inview and st["count"]:
+        items = sum(inview) / len(inview)
+        l1_bytes = items * (768 * 64 + 36 * 384)
+        sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
+        l1_peak = 148 * 64 * sm_mhz * 1e6 / 1e9
+        l1 = {"bound": "l1-ldg", "in_view_items_per_launch": items, "in_view_fraction": items / (B * V * n_pts),
+              "gathered_bytes_per_launch": int(l1_bytes),
+              "achieved": l1_bytes / (st["mean_ms"] * 1e-3) / 1e9, "peak": l1_peak, "unit": "GB/s",
+              "frac": l1_bytes / (st["mean_ms"] * 1e-3) / 1e9 / l1_peak,
+              "peak_source": "148 SMs x 64 B/clk (measured LDG.128 hit rate, profiles/ubench_l1_mma_r1.txt) x sampled SM clock"}
     roofline = {"kernel": "mvg::gather_kernel<3> (+ project_compact_kernel)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "algorithmic_bytes_per_launch": int(alg_bytes),
                 "launch_ms": st["mean_ms"], "launches_timed": st["count"], "peak_source": peak_src,
+                "l1": l1,
                 "stage_ms_per_step": {k: v["total_ms"] / prof_steps for k, v in sorted(stages.items())}}
+
+    # ---- the steps either side of the decoder, device time
+    pre_post = None
+    if world == 1:
+        from mvgformer_b200 import postprocess as post
+        qi = mvg.QueryInit(Q, J, 256, sc["space_size"], sc["space_center"]).to(dev)
+        poses, prob = forward_resident()
+        poses, prob = poses.clone(), prob.clone()
+
+        def t_ms(fn, n=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            for _ in range(n):
+                fn()
+            e_.record()
+            torch.cuda.synchronize()
+            return s_.elapsed_time(e_) / n
+
+        def run_post():
+            pred, vid, vcnt = post.assemble_predictions(poses, prob, a.threshold, J)
+            return post.nearby_joints_nms(pred, vid, vcnt, 0.3, 7)
+
+        kept = int(run_post()[2][0])
+        pre_post = {"init_queries_ms": t_ms(lambda: qi(B)), "assemble_filter_nms_ms": t_ms(run_post),
+                    "poses_kept_by_nms_frame0": kept,
+                    "note": "device time of mvg_init_queries and mvg_assemble_predictions + "
+                            "mvg_nearby_joints_nms on the step's outputs; not part of `value`"}
 
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -431,7 +477,8 @@ def run_ours(a):
             "data": "synthetic", "config": workload_config(a, world),
             "gemm_backend": mlinear.get_backend(), "gpu_launches": int(launches_per_step),
             "launch_mode": "eager" if graphed is None else "cuda-graph replay",
-            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "pre_post": pre_post,
+            "weight_pack_misses": prof.counters().get("weight_pack_misses", 0),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

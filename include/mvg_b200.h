@@ -211,6 +211,21 @@ MVG_API int mvg_add_cast_bf16(const float* a, const float* b, void* out_bf16, in
 MVG_API int mvg_class_head(const float* x, const float* w, const float* bias, int batch, int queries,
                    int joints, float* prob, void* stream);
 
+/* Fused query-feature update of one decoder layer (dq_decoder.py:770-778 'MLP' branch +
+ * forward_ffn, mvp_decoder.py:94-98), one kernel, activations resident on chip:
+ *   tu  = LayerNorm(tgt + aver @ w_fu^T + b_fu; g2, e2, eps2)
+ *   out = LayerNorm(tu + relu(tu @ w1^T + b1) @ w2^T + b2; g3, e3, eps3)
+ * aver (M,256) bf16 (mvg_masked_view_mean output), tgt (M,256) fp32, w_fu (256,256), w1
+ * (d_ffn,256), w2 (256,d_ffn) bf16 row-major (nn.Linear layout), biases / LayerNorm parameters
+ * fp32, out (M,256) fp32.  d_model is 256, d_ffn a multiple of 256.  Dropout is identity
+ * (inference).  GEMMs on tcgen05 with fp32 accumulation; t2 and the FFN output are NOT rounded
+ * to bf16 (the unfused path does round them).
+ */
+MVG_API int mvg_ffn_chain(const void* aver_bf16, const float* tgt, const void* w_fu, const float* b_fu,
+                  const float* g2, const float* e2, float eps2, const void* w1, const float* b1,
+                  const void* w2, const float* b2, const float* g3, const float* e3, float eps3,
+                  int64_t M, int d_ffn, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * The steps either side of the decoder.
  *

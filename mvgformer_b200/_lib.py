@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("MVG_LIB_PATH", os.path.join(_HERE, "libmvg_b200.so"))
 MVG_F32, MVG_BF16 = 0, 1
 MVG_MAX_LEVELS = 4
 MVG_CAM_FLOATS = 64
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class MvgError(RuntimeError):
@@ -54,6 +54,7 @@ SIGNATURES = {
     "mvg_class_prob": [_P, _I, _I, _I, _P, _P],
     "mvg_add_cast_bf16": [_P, _P, _P, _L, _P],
     "mvg_class_head": [_P, _P, _P, _I, _I, _I, _P, _P],
+    "mvg_ffn_chain": [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _F, _L, _I, _P, _P],
     "mvg_init_queries": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "mvg_assemble_predictions": [_P, _P, _I, _I, _I, _F, _P, _P, _P, _P],
     "mvg_nearby_joints_nms": [_P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P],

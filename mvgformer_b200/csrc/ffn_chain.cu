@@ -1,0 +1,398 @@
+// Fused query-feature update (dq_decoder.py:770-778 'MLP' branch + forward_ffn,
+// mvp_decoder.py:94-98) for one 128-row tile of points, all on chip:
+//
+//   t2  = aver @ Wfu^T + bfu                      tcgen05, fp32 accumulator in TMEM
+//   tu  = LayerNorm2(tgt + t2)                    epilogue: row statistics straight from TMEM
+//   h_c = relu(tu @ W1[c]^T + b1[c])   c = 0..3   hidden layer in 256-column chunks, bf16 in smem
+//   y  += h_c @ W2[:, c]^T                        second accumulator in TMEM
+//   out = LayerNorm3(tu + y + b2)
+//
+// Before this kernel the chain was 6 launches (3 GEMMs + 2 LayerNorm kernels + their bf16 / fp32
+// round trips through HBM, 73 us per layer at M = 15 360); here the activations never leave the
+// SM: the A operand of every GEMM is written by the previous epilogue directly in the
+// K-major / SWIZZLE_128B layout the UMMA descriptors expect, t2 and y stay fp32 (the unfused
+// path rounded both to bf16), and only the weights stream from L2 (1.15 MB per tile, 32 KB
+// TMA stages).  One CTA per tile (120 tiles for Q = 1024), 10 warps:
+//   warp 0      TMA producer: the aver tile (4 K-panels of 128 x 64) + 36 weight stages
+//   warp 1      TMEM owner + single-thread tcgen05.mma issue (M = 128, N = 256, K = 16)
+//   warps 2-9   epilogues; warp w owns TMEM lanes 32 (w % 4) .. +31 and one 128-column half,
+//               the two warps of a row group exchange LayerNorm partial sums through smem
+#include "tcgen05.cuh"
+
+namespace mvg {
+
+constexpr int kFcStages = 3;
+constexpr int kFcStageBytes = 256 * kBlockK * 2;        // 32 KB: 256 weight rows x 64 K
+constexpr int kFcPanelBytes = kBlockM * kBlockK * 2;    // 16 KB: 128 rows x 64 K
+constexpr int kFcActBytes = 4 * kFcPanelBytes;          // 64 KB: a 128 x 256 bf16 activation tile
+constexpr int kFcThreads = 10 * 32;
+constexpr int kFcSmemBytes = 2 * kFcActBytes + kFcStages * kFcStageBytes + 2048 /*stats*/ + 256 /*barriers*/;
+static_assert(kFcSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+constexpr int kFcD = 256;                               // d_model
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+      "%13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void pair_barrier(int id) {   // the two epilogue warps of a row group
+  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+
+// 16 fp32 values of row r, columns [col, col + 16) -> bf16 -> K-major SWIZZLE_128B activation tile
+__device__ __forceinline__ void store_act16(uint8_t* act, int r, int col, const float* v) {
+  uint8_t* rowp = act + (col >> 6) * kFcPanelBytes + r * 128;
+  const int j0 = (col & 63) >> 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint4 o;
+    o.x = pack_bf16x2(v[8 * h + 0], v[8 * h + 1]); o.y = pack_bf16x2(v[8 * h + 2], v[8 * h + 3]);
+    o.z = pack_bf16x2(v[8 * h + 4], v[8 * h + 5]); o.w = pack_bf16x2(v[8 * h + 6], v[8 * h + 7]);
+    *reinterpret_cast<uint4*>(rowp + (((j0 + h) ^ (r & 7)) << 4)) = o;
+  }
+}
+
+struct FfnChainParams {
+  const float* tgt;        // (M, 256) fp32
+  const float* b_fu;       // (256)
+  const float* g2;         // LayerNorm2 weight / bias
+  const float* e2;
+  const float* b1;         // (d_ffn)
+  const float* b2;         // (256)
+  const float* g3;
+  const float* e3;
+  float* out;              // (M, 256) fp32; also holds tu between the two LayerNorms
+  int M;
+  int n_chunks;            // d_ffn / 256
+  float eps2, eps3;
+};
+
+// x = acc + bias + residual for this warp's 128 columns of row r, written back to TMEM; returns the
+// partial sum / sum of squares.  The residual row is fetched 64 columns at a time (16 independent
+// 16-byte loads in flight per thread - a row per thread is an uncoalesced but sector-exact pattern).
+template <bool kLdg>
+__device__ __forceinline__ void tmem_add_residual(uint32_t taddr, int half, const float* __restrict__ bias,
+                                                  const float* res_row, bool row_ok, float& s, float& ss) {
+  s = 0.f; ss = 0.f;
+#pragma unroll 1
+  for (int c4 = 0; c4 < 2; ++c4) {
+    const int col0 = half * 128 + c4 * 64;
+    float4 t[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_ok) {
+        if (kLdg) t[i] = __ldg(reinterpret_cast<const float4*>(res_row + col0) + i);
+        else t[i] = *(reinterpret_cast<const float4*>(res_row + col0) + i);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = col0 + j * 16;
+      uint32_t u[16];
+      tmem_ld16(taddr + col, u);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col + i));
+        const float4 t4 = t[j * 4 + (i >> 2)];
+        const float x0 = __uint_as_float(u[i + 0]) + b4.x + t4.x, x1 = __uint_as_float(u[i + 1]) + b4.y + t4.y;
+        const float x2 = __uint_as_float(u[i + 2]) + b4.z + t4.z, x3 = __uint_as_float(u[i + 3]) + b4.w + t4.w;
+        s += (x0 + x1) + (x2 + x3);
+        ss += (x0 * x0 + x1 * x1) + (x2 * x2 + x3 * x3);
+        u[i + 0] = __float_as_uint(x0); u[i + 1] = __float_as_uint(x1);
+        u[i + 2] = __float_as_uint(x2); u[i + 3] = __float_as_uint(x3);
+      }
+      tmem_st16(taddr + col, u);
+    }
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// LayerNorm over the 256 columns of a row whose pre-norm values sit in TMEM columns
+// [taddr, taddr + 256) of this thread's lane.  `half` selects this warp's 128 columns; the partner
+// warp (same lanes, other half) contributes its partial (sum, sum of squares) through `stats`.
+// Variance = E[x^2] - mean^2 in fp32 (|mean| <~ std for these rows).  fn(col, y[16]) consumes
+// the normalised values.
+template <typename F>
+__device__ __forceinline__ void tmem_layernorm(uint32_t taddr, int half, int r, int pair_id, float2* stats,
+                                               float s, float ss, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, float eps, F&& fn) {
+  stats[half * 128 + r] = make_float2(s, ss);
+  pair_barrier(pair_id);
+  const float2 o = stats[(half ^ 1) * 128 + r];
+  pair_barrier(pair_id);                                   // both reads done before the next use
+  const float mean = (s + o.x) * (1.f / 256.f);
+  const float var = fmaxf((ss + o.y) * (1.f / 256.f) - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+#pragma unroll 2
+  for (int cc = 0; cc < 8; ++cc) {
+    const int col = half * 128 + cc * 16;
+    uint32_t u[16];
+    tmem_ld16(taddr + col, u);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float y[16];
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col + i));
+      const float4 e = __ldg(reinterpret_cast<const float4*>(beta + col + i));
+      y[i + 0] = (__uint_as_float(u[i + 0]) - mean) * rstd * g.x + e.x;
+      y[i + 1] = (__uint_as_float(u[i + 1]) - mean) * rstd * g.y + e.y;
+      y[i + 2] = (__uint_as_float(u[i + 2]) - mean) * rstd * g.z + e.z;
+      y[i + 3] = (__uint_as_float(u[i + 3]) - mean) * rstd * g.w + e.w;
+    }
+    fn(col, y);
+  }
+}
+
+__global__ void __launch_bounds__(kFcThreads, 1)
+ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_fu,
+                 const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
+                 const FfnChainParams p) {
+  // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked),
+  // which SWIZZLE_128B tiles need; there is no room left for an alignment slack
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* xbuf = smem;                                  // aver tile, then tu (bf16)
+  uint8_t* hbuf = smem + kFcActBytes;                    // relu(hidden chunk) (bf16)
+  uint8_t* wbuf = smem + 2 * kFcActBytes;                // weight ring
+  float2* stats = reinterpret_cast<float2*>(wbuf + kFcStages * kFcStageBytes);   // [2][128] (sum, sumsq)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats) + 2048);
+  uint64_t* w_full = bars;                   // [kFcStages]
+  uint64_t* w_empty = bars + kFcStages;      // [kFcStages]
+  uint64_t* x_full = bars + 2 * kFcStages;
+  uint64_t* x_free = x_full + 1;
+  uint64_t* acc1_full = x_full + 2;
+  uint64_t* acc2_full = x_full + 3;
+  uint64_t* acc2_free = x_full + 4;
+  uint64_t* tu_ready = x_full + 5;
+  uint64_t* h_ready = x_full + 6;
+  uint64_t* h_free = x_full + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int NCH = p.n_chunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_fu)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w1)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w2)) : "memory");
+    for (int s = 0; s < kFcStages; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    mbar_init(x_full, 1);
+    mbar_init(x_free, 1);
+    mbar_init(acc1_full, 1);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_free, 8);
+    mbar_init(tu_ready, 8);
+    mbar_init(h_ready, 8);
+    mbar_init(h_free, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc1 = tmem_base, acc2 = tmem_base + 256;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t ws = 0, it = 0;
+      auto load_w = [&](const CUtensorMap* map, int c0, int c1) {
+        const int s = ws % kFcStages;
+        mbar_wait(&w_empty[s], ((ws / kFcStages) & 1) ^ 1);
+        mbar_expect_tx(&w_full[s], kFcStageBytes);
+        tma_load_2d(map, &w_full[s], wbuf + s * kFcStageBytes, c0, c1);
+        ++ws;
+      };
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+        if (it > 0) mbar_wait(x_free, (it - 1) & 1);      // previous tile's MMAs are done with xbuf
+        mbar_expect_tx(x_full, kFcActBytes);
+        for (int kb = 0; kb < 4; ++kb)
+          tma_load_2d(&tmap_x, x_full, xbuf + kb * kFcPanelBytes, kb * kBlockK, mt * kBlockM);
+        for (int kb = 0; kb < 4; ++kb) load_w(&tmap_fu, kb * kBlockK, 0);
+        for (int c = 0; c < NCH; ++c) {
+          for (int kb = 0; kb < 4; ++kb) load_w(&tmap_w1, kb * kBlockK, c * 256);
+          for (int kb = 0; kb < 4; ++kb) load_w(&tmap_w2, c * 256 + kb * kBlockK, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(256);
+      uint32_t ws = 0, it = 0, hc = 0;
+      // one 128 x 256 x 256 GEMM: A = 4 K-panels at `abuf`, B = the next 4 weight stages
+      auto gemm = [&](uint8_t* abuf, uint32_t tmem_d, bool fresh) {
+        for (int kb = 0; kb < 4; ++kb, ++ws) {
+          const int s = ws % kFcStages;
+          mbar_wait(&w_full[s], (ws / kFcStages) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_smem_desc_sw128(smem_u32(abuf + kb * kFcPanelBytes));
+          const uint64_t db = make_smem_desc_sw128(smem_u32(wbuf + s * kFcStageBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                      (!fresh || (kb | k) != 0) ? 1u : 0u);
+          umma_commit(&w_empty[s]);
+        }
+      };
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+        mbar_wait(x_full, it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        gemm(xbuf, acc1, true);                          // t2
+        umma_commit(acc1_full);
+        mbar_wait(tu_ready, it & 1);                     // LayerNorm2 wrote tu into xbuf, acc1 is free
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c = 0; c < NCH; ++c, ++hc) {
+          gemm(xbuf, acc1, true);                        // hidden chunk c
+          umma_commit(acc1_full);
+          if (c == NCH - 1) umma_commit(x_free);
+          mbar_wait(h_ready, hc & 1);                    // relu(h_c) is in hbuf, acc1 is free
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (c == 0 && it > 0) {
+            mbar_wait(acc2_free, (it - 1) & 1);          // previous tile's LayerNorm3 has drained acc2
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          gemm(hbuf, acc2, c == 0);                      // y += h_c W2[:, c]^T
+          umma_commit(h_free);
+        }
+        umma_commit(acc2_full);
+      }
+    }
+  } else {
+    // ===================== epilogues (warps 2..9) =====================
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                     // column half
+    const int r = q * 32 + lane;                          // row inside the tile
+    const int pair_id = 1 + q;
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t it = 0, a1 = 0, hc = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+      const int row = mt * kBlockM + r;
+      const bool row_ok = row < p.M;
+      const float* trow = p.tgt + static_cast<int64_t>(row) * kFcD;
+      float* orow = p.out + static_cast<int64_t>(row) * kFcD;
+      // ---- LayerNorm2(tgt + t2): x = acc1 + bfu + tgt written back to TMEM, then normalised
+      mbar_wait(acc1_full, a1 & 1); ++a1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float s_, ss_;
+      tmem_add_residual<true>(acc1 + lane_sel, half, p.b_fu, trow, row_ok, s_, ss_);
+      tmem_layernorm(acc1 + lane_sel, half, r, pair_id, stats, s_, ss_, p.g2, p.e2, p.eps2,
+                     [&](int col, const float* y) {
+                       if (row_ok) {
+#pragma unroll
+                         for (int i = 0; i < 16; i += 4)
+                           *reinterpret_cast<float4*>(orow + col + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+                       }
+                       store_act16(xbuf, r, col, y);
+                     });
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tu_ready);
+      // ---- hidden chunks: relu(acc1 + b1) -> hbuf
+      for (int c = 0; c < NCH; ++c, ++hc) {
+        mbar_wait(acc1_full, a1 & 1); ++a1;
+        if (hc > 0) mbar_wait(h_free, (hc - 1) & 1);      // the previous y GEMM has read hbuf
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int cc = 0; cc < 8; ++cc) {
+          const int col = half * 128 + cc * 16;
+          uint32_t u[16];
+          tmem_ld16(acc1 + lane_sel + col, u);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b1 + c * 256 + col + i));
+            v[i + 0] = fmaxf(__uint_as_float(u[i + 0]) + b4.x, 0.f);
+            v[i + 1] = fmaxf(__uint_as_float(u[i + 1]) + b4.y, 0.f);
+            v[i + 2] = fmaxf(__uint_as_float(u[i + 2]) + b4.z, 0.f);
+            v[i + 3] = fmaxf(__uint_as_float(u[i + 3]) + b4.w, 0.f);
+          }
+          store_act16(hbuf, r, col, v);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h_ready);
+      }
+      // ---- LayerNorm3(tu + y + b2)
+      mbar_wait(acc2_full, it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tmem_add_residual<false>(acc2 + lane_sel, half, p.b2, orow, row_ok, s_, ss_);   // + tu, written by this thread
+      tmem_layernorm(acc2 + lane_sel, half, r, pair_id, stats, s_, ss_, p.g3, p.e3, p.eps3,
+                     [&](int col, const float* y) {
+                       if (row_ok) {
+#pragma unroll
+                         for (int i = 0; i < 16; i += 4)
+                           *reinterpret_cast<float4*>(orow + col + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+                       }
+                     });
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc2_free);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace mvg
+
+extern "C" int mvg_ffn_chain(const void* aver_bf16, const float* tgt, const void* w_fu, const float* b_fu,
+                             const float* g2, const float* e2, float eps2, const void* w1, const float* b1,
+                             const void* w2, const float* b2, const float* g3, const float* e3, float eps3,
+                             int64_t M, int d_ffn, float* out, void* stream) {
+  using namespace mvg;
+  MVG_REQUIRE(aver_bf16 && tgt && w_fu && b_fu && g2 && e2 && w1 && b1 && w2 && b2 && g3 && e3 && out,
+              "mvg_ffn_chain: null pointer");
+  MVG_REQUIRE(M > 0 && M < (1ll << 31), "mvg_ffn_chain: bad M");
+  MVG_REQUIRE(d_ffn >= 256 && d_ffn % 256 == 0, "mvg_ffn_chain: d_ffn=%d must be a multiple of 256", d_ffn);
+  const void* ptrs[] = {aver_bf16, tgt, w_fu, b_fu, g2, e2, w1, b1, w2, b2, g3, e3, out};
+  for (const void* q : ptrs)
+    MVG_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0, "mvg_ffn_chain: operands must be 16-byte aligned");
+  CUtensorMap tx, tfu, tw1, tw2;
+  int rc = make_tmap(&tx, aver_bf16, M, kFcD, kBlockM);
+  if (rc) return rc;
+  rc = make_tmap(&tfu, w_fu, kFcD, kFcD, 256);
+  if (rc) return rc;
+  rc = make_tmap(&tw1, w1, d_ffn, kFcD, 256);
+  if (rc) return rc;
+  rc = make_tmap(&tw2, w2, kFcD, d_ffn, 256);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ffn_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%d): %s", kFcSmemBytes, cudaGetErrorString(e));
+      return MVG_ELAUNCH;
+    }
+    attr_set = true;
+  }
+  FfnChainParams p{tgt, b_fu, g2, e2, b1, b2, g3, e3, out, static_cast<int>(M), d_ffn / 256, eps2, eps3};
+  const int m_tiles = static_cast<int>((M + kBlockM - 1) / kBlockM);
+  const int grid = m_tiles < kNumSMs ? m_tiles : kNumSMs;
+  ffn_chain_kernel<<<grid, kFcThreads, kFcSmemBytes, static_cast<cudaStream_t>(stream)>>>(tx, tfu, tw1, tw2, p);
+  return check_launch("mvg_ffn_chain");
+}

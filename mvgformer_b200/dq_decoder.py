@@ -57,6 +57,14 @@ class offset_net(nn.Module):
         self.MLP = MLP(in_dim, hid_dim, 3, layer_num)
 
 
+def _use_ffn_chain() -> bool:
+    """The fused update kernel needs the tcgen05 GEMM backend; MVG_FFN_CHAIN=0 selects the
+    unfused chain (A/B measurements, cuBLAS comparison backend)."""
+    import os
+    from .linear import get_backend
+    return os.environ.get("MVG_FFN_CHAIN", "1") != "0" and get_backend() == "tcgen05"
+
+
 def _get_clones(module, N):
     return nn.ModuleList([copy.deepcopy(module) for _ in range(N)])
 
@@ -67,14 +75,20 @@ class DecoderContext:
 
     def __init__(self, src_views: Sequence[torch.Tensor], meta: List[Dict], img_size,
                  layers: Sequence["DQDecoderLayer"], batch_size: int):
-        dev = src_views[0].device
-        self.levels = [(int(s.shape[2]), int(s.shape[3])) for s in src_views]
+        if isinstance(src_views, ops.PackedPyramid):      # already channels-last bf16: zero-copy
+            dev, feat_cl = src_views.feat.device, src_views.feat
+            self.levels = list(src_views.levels)
+            rows = feat_cl.shape[0]
+        else:
+            dev = src_views[0].device
+            self.levels = [(int(s.shape[2]), int(s.shape[3])) for s in src_views]
+            rows = src_views[0].shape[0]
+            with prof.stage("pyramid_to_cl"):
+                feat_cl = ops.pyramid_to_channels_last(src_views)            # (V*B,S,256) bf16
         self.batch = batch_size
-        self.views = src_views[0].shape[0] // batch_size
+        self.views = rows // batch_size
         self.img_size = [float(img_size[0]), float(img_size[1])]
         self.cams = pack_cameras(meta, img_size, device=dev)                 # (B,V,64)
-        with prof.stage("pyramid_to_cl"):
-            feat_cl = ops.pyramid_to_channels_last(src_views)                # (V*B,S,256) bf16
         # one GEMM for all distinct layers: the pyramid is read from HBM once
         distinct: List[DQDecoderLayer] = []
         for l in layers:
@@ -180,6 +194,7 @@ class DQDecoderLayer(nn.Module):
         key = tuple((p.data_ptr(), p._version, p.device) for p in ps)
         if self._wcache is not None and self._wcache[0] == key:
             return self._wcache[1]
+        prof.count("weight_pack_misses")
         bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
         f32 = lambda t: t.detach().float().contiguous()
         with torch.no_grad():
@@ -222,17 +237,24 @@ class DQDecoderLayer(nn.Module):
         prm = ops.make_sample_params(B, V, N, ctx.levels, ctx.ld_vg, ctx.img_size)
         with prof.stage("project_sample_fused"):
             sampled, ref2d, bounding = ops.project_sample_fused(ref3d, ctx.cams, vg, qproj, prm)
+        prof.note("inview_items", ops._last_work[0])       # no-op unless profiling is enabled
         # 4. output_proj, mask, view-mean, update MLP, LN, FFN, LN
         with prof.stage("output_proj"):
             # (B,V,N,256) bf16, rows of out-of-view points zeroed in the epilogue (:585-586)
             attn = linear(sampled, pw["w_o"], pw["b_o"], row_mask=bounding)
         with prof.stage("update_feature"):
             aver = ops.masked_view_mean(attn, bounding)                           # :770
-            t2 = linear(aver, lw["w_fu"], lw["b_fu"])
-            tu, tu_bf = ops.add_layernorm(tgt, t2, lw["g2"], lw["e2"], self.norm2.eps)
-            hdn = linear(tu_bf, lw["w1"], lw["b1"], relu=True)
-            ff = linear(hdn, lw["w2"], lw["b2"])
-            tgt_update, _ = ops.add_layernorm(tu, ff, lw["g3"], lw["e3"], self.norm3.eps, want_bf16=False)
+            if _use_ffn_chain() and self.d_ffn % 256 == 0:
+                # feature_update_mlp + norm2 + FFN + norm3 in one kernel (csrc/ffn_chain.cu)
+                tgt_update = ops.ffn_chain(aver, tgt, lw["w_fu"], lw["b_fu"], lw["g2"], lw["e2"],
+                                           self.norm2.eps, lw["w1"], lw["b1"], lw["w2"], lw["b2"],
+                                           lw["g3"], lw["e3"], self.norm3.eps)
+            else:
+                t2 = linear(aver, lw["w_fu"], lw["b_fu"])
+                tu, tu_bf = ops.add_layernorm(tgt, t2, lw["g2"], lw["e2"], self.norm2.eps)
+                hdn = linear(tu_bf, lw["w1"], lw["b1"], relu=True)
+                ff = linear(hdn, lw["w2"], lw["b2"])
+                tgt_update, _ = ops.add_layernorm(tu, ff, lw["g3"], lw["e3"], self.norm3.eps, want_bf16=False)
         # 5. class head + query filter (integer path)
         with prof.stage("class_head"):
             prob = ops.class_head(tgt_update, lw["wc"], lw["bc"], Q, J)           # (B,Q,2)

@@ -31,6 +31,28 @@ def pyramid_to_channels_last(src_views: Sequence[torch.Tensor]) -> torch.Tensor:
     return dst
 
 
+class PackedPyramid:
+    """The decoder's on-device pyramid format: ONE channels-last bf16 matrix (V*B, S, C), level l
+    at positions [start_l, start_l + H_l*W_l), rows view-major (r = v*B + b) like the reference's
+    `src_views` (dq_transformer.py:352-354).  A backbone head that writes its three deconv
+    outputs straight into `feat` hands them to `DQDecoder.forward`
+    with no permute / copy: pass the PackedPyramid in place of the `src_views` list."""
+
+    def __init__(self, feat: torch.Tensor, levels: Sequence[Tuple[int, int]]):
+        if feat.dim() != 3 or feat.dtype != torch.bfloat16 or not feat.is_contiguous():
+            raise _lib.MvgError("PackedPyramid: feat must be a contiguous (rows, S, C) bfloat16 tensor")
+        if sum(h * w for h, w in levels) != feat.shape[1]:
+            raise _lib.MvgError("PackedPyramid: sum(H_l * W_l) != S")
+        _lib.require_cuda(feat)
+        self.feat = feat
+        self.levels = [(int(h), int(w)) for h, w in levels]
+
+    @classmethod
+    def from_nchw(cls, src_views: Sequence[torch.Tensor]) -> "PackedPyramid":
+        return cls(pyramid_to_channels_last(src_views),
+                   [(int(s.shape[2]), int(s.shape[3])) for s in src_views])
+
+
 def linear_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *,
                 relu: bool = False, out_dtype=torch.bfloat16,
                 out: Optional[torch.Tensor] = None,
@@ -46,6 +68,9 @@ def linear_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
                               dtype_code(out.dtype), M, nout, K, out.stride(-2) if out.dim() > 1 else nout,
                               1 if relu else 0, _lib.ptr(row_mask), stream_ptr(a.device)), "mvg_linear_bf16")
     return out
+
+
+_last_work: Optional[torch.Tensor] = None
 
 
 def make_sample_params(batch: int, views: int, points: int, levels: Sequence[Tuple[int, int]],
@@ -79,6 +104,8 @@ def project_sample_fused(ref3d: Optional[torch.Tensor], cams: Optional[torch.Ten
                                        qproj.data_ptr(), C.byref(prm), sampled.data_ptr(),
                                        ref2d.data_ptr(), bounding.data_ptr(), _lib.ptr(refl),
                                        _lib.ptr(work), stream_ptr(dev)), "mvg_project_sample_fused")
+    global _last_work
+    _last_work = work          # diagnostics only (profiling.note in dq_decoder): [0] = in-view items
     return sampled, ref2d, bounding
 
 
@@ -185,4 +212,19 @@ def add_cast_bf16(a: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
     out = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
     check(lib.mvg_add_cast_bf16(a.data_ptr(), _lib.ptr(b), out.data_ptr(), a.numel(),
                                 stream_ptr(a.device)), "mvg_add_cast_bf16")
+    return out
+
+
+def ffn_chain(aver: torch.Tensor, tgt: torch.Tensor, w_fu, b_fu, g2, e2, eps2, w1, b1, w2, b2, g3, e3,
+              eps3) -> torch.Tensor:
+    """LayerNorm(tu + FFN(tu)), tu = LayerNorm(tgt + aver @ w_fu^T + b_fu) in one tcgen05 kernel.
+    aver (..., 256) bf16, tgt (..., 256) fp32 -> (..., 256) fp32."""
+    lib = _lib.load()
+    _lib.require_cuda(aver, tgt)
+    M = aver.numel() // aver.shape[-1]
+    out = torch.empty(tgt.shape, dtype=torch.float32, device=tgt.device)
+    check(lib.mvg_ffn_chain(aver.data_ptr(), tgt.data_ptr(), w_fu.data_ptr(), b_fu.data_ptr(), g2.data_ptr(),
+                            e2.data_ptr(), float(eps2), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                            b2.data_ptr(), g3.data_ptr(), e3.data_ptr(), float(eps3), M, int(w1.shape[0]),
+                            out.data_ptr(), stream_ptr(tgt.device)), "mvg_ffn_chain")
     return out

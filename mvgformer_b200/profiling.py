@@ -11,6 +11,7 @@ import torch
 
 _enabled = False
 _events: Dict[str, List] = defaultdict(list)
+_notes: Dict[str, List] = defaultdict(list)
 
 
 def enable(flag: bool = True) -> None:
@@ -20,6 +21,32 @@ def enable(flag: bool = True) -> None:
 
 def reset() -> None:
     _events.clear()
+    _notes.clear()
+
+
+_counters: Dict[str, int] = defaultdict(int)
+
+
+def count(name: str, n: int = 1) -> None:
+    """Host-side event counter (always on): e.g. weight re-packs, which must stay at one per
+    module for the life of a model."""
+    _counters[name] += n
+
+
+def counters() -> Dict[str, int]:
+    return dict(_counters)
+
+
+def note(name: str, value: torch.Tensor) -> None:
+    """Keeps a (cloned) device scalar for later inspection, e.g. the number of in-view items the
+    gather processed; no synchronisation happens here."""
+    if _enabled:
+        _notes[name].append(value.detach().clone())
+
+
+def notes() -> Dict[str, List[float]]:
+    """name -> list of recorded values; call after torch.cuda.synchronize()."""
+    return {k: [float(t) for t in v] for k, v in _notes.items()}
 
 
 @contextmanager

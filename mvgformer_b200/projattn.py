@@ -22,6 +22,7 @@ from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
 from . import ops
+from . import profiling as prof
 from .linear import linear
 
 
@@ -98,6 +99,7 @@ class ProjAttn(nn.Module):
         key = tuple((p.data_ptr(), p._version, p.device) for p in ps)
         if self._wcache is not None and self._wcache[0] == key:
             return self._wcache[1]
+        prof.count("weight_pack_misses")
         with torch.no_grad():
             w_q = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
             b_q = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0).float()

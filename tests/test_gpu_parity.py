@@ -388,6 +388,16 @@ def test_decoder_forward_api_and_stack():
                           scd["src_views"], scd["spatial_shapes"], scd["level_start_index"],
                           scd["meta"], threshold=SMALL["threshold"])
     assert torch.equal(o[0], hs[0]) and torch.equal(o[1], refs[0])
+    # section 8f row 4: a channels-last bf16 pyramid is consumed in place (no permute / copy)
+    packed = ops.PackedPyramid.from_nchw(scd["src_views"])
+    assert packed.feat.shape == (V * B, sum(h * w for h, w in SMALL["levels"]), 256)
+    with torch.no_grad():
+        hs_p, refs_p, _, _, cls_p = dec(scd["tgt"], scd["reference_points"], packed, scd["meta"],
+                                        scd["spatial_shapes"], scd["level_start_index"], None,
+                                        query_pos=scd["query_pos"], threshold=SMALL["threshold"])
+    assert torch.equal(hs_p, hs) and torch.equal(refs_p, refs) and torch.equal(cls_p[-1], cls[-1])
+    with pytest.raises(mvg._lib.MvgError):
+        ops.PackedPyramid(packed.feat.float(), SMALL["levels"])
 
 
 def test_full_size_properties():
@@ -639,6 +649,31 @@ def test_linear_tcgen05(M, N, K, relu, out_dtype):
     mask = torch.from_numpy(rng.integers(0, 2, size=M).astype(np.uint8)).to(DEV)
     outm = ops.linear_bf16(a, w, b, relu=relu, out_dtype=out_dtype, row_mask=mask)
     assert torch.equal(outm, out * mask[:, None].to(out.dtype))
+
+
+@pytest.mark.parametrize("M,d_ffn", [(300, 1024), (15360, 1024), (148 * 128 * 2 + 5, 512)])
+def test_ffn_chain_vs_fp32(M, d_ffn):
+    """mvg_ffn_chain (feature_update_mlp + norm2 + FFN + norm3 in one tcgen05 kernel) vs the same
+    chain in fp64 torch on the bf16-rounded operands; bf16 roundings left inside the kernel:
+    tu and relu(h) as MMA operands.  Also: partial last tile, several tiles per CTA."""
+    rng = np.random.default_rng(M)
+    f = lambda *sh, sc=1.0: torch.from_numpy((rng.standard_normal(sh) * sc).astype(np.float32))
+    aver, tgt = bf16_round(f(M, 256)), f(M, 256)
+    w_fu, w1, w2 = bf16_round(f(256, 256, sc=1 / 16)), bf16_round(f(d_ffn, 256, sc=1 / 16)), \
+        bf16_round(f(256, d_ffn, sc=1 / 32))
+    b_fu, b1, b2 = f(256, sc=0.1), f(d_ffn, sc=0.1), f(256, sc=0.1)
+    g2, e2, g3, e3 = 1 + f(256, sc=0.1), f(256, sc=0.1), 1 + f(256, sc=0.1), f(256, sc=0.1)
+    D = lambda t: t.to(DEV)
+    out = ops.ffn_chain(D(aver).bfloat16(), D(tgt), D(w_fu).bfloat16(), D(b_fu), D(g2), D(e2), 1e-5,
+                        D(w1).bfloat16(), D(b1), D(w2).bfloat16(), D(b2), D(g3), D(e3), 1e-5).cpu()
+    LN = torch.nn.functional.layer_norm
+    d = lambda t: t.double()
+    tu = LN(d(tgt) + d(aver) @ d(w_fu).t() + d(b_fu), (256,), d(g2), d(e2), 1e-5)
+    h = torch.relu(bf16_round(tu.float()).double() @ d(w1).t() + d(b1))
+    ref = LN(tu + bf16_round(h.float()).double() @ d(w2).t() + d(b2), (256,), d(g3), d(e3), 1e-5)
+    err = (out.double() - ref).abs()
+    assert torch.isfinite(out).all()
+    assert float(err.max()) < 2e-2 and float(err.mean()) < 1.5e-3, (float(err.max()), float(err.mean()))
 
 
 def test_decoder_tcgen05_matches_cublas_backend():

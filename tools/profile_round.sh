@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round evidence (run on the GPU box): tests, bench line, ncu launch list, ncu --set full of one step.
+#   gpurun -- 'bash tools/profile_round.sh r1'
+tag=${1:-r1}
+mkdir -p gpurun_out
+(timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "exit $?" >> gpurun_out/pytest_gpu_$tag.log)
+tail -3 gpurun_out/pytest_gpu_$tag.log
+timeout 600 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
+cat gpurun_out/bench_$tag.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 400 --csv \
+  --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-graph \
+  > gpurun_out/launches_$tag.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:mvg -s 225 -c 75 -o gpurun_out/step_$tag \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-graph > gpurun_out/step_$tag.log 2>&1
+tail -2 gpurun_out/step_$tag.log | cut -c1-200
+ls -la gpurun_out/
