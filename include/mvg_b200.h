@@ -109,6 +109,16 @@ MVG_API int mvg_linear_bf16(const void* A, const void* W, const float* bias, voi
                     int64_t M, int Nout, int K, int64_t ldo, int relu, const uint8_t* row_mask,
                     void* stream);
 
+/* Value / offset / logit projection of the channels-last pyramid for ALL decoder layers in one
+ * tcgen05 GEMM (rayconv + the per-level sampling_offsets / attention_weights Linears,
+ * projattn.py:169,180-181), written in the layouts the fused gather reads:
+ *   feat (M = V*B*S, 256) bf16; W (layers*448, 256) bf16, per layer rows [rayconv 256 |
+ *   sampling_offsets 128 | attention_weights 64]; bias (layers*448) fp32 or NULL;
+ *   value_hm (layers*8, M, 32) bf16 head-major; gmap (M, layers*192) bf16.
+ */
+MVG_API int mvg_value_proj_gemm(const void* feat, const void* W, const float* bias, int64_t M, int layers,
+                        void* value_hm, void* gmap, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Fused projection + projective attention sampling for all (b, v, n):
  *   a3  project_ref_points   (dq_decoder.py:331-397, cameras.py:167-207, transforms.py:135-141)
@@ -117,9 +127,12 @@ MVG_API int mvg_linear_bf16(const void* A, const void* W, const float* bias, voi
  *   a5  multi-scale deformable gather (deform_im2col_cuda.cuh:247-309)
  * Inputs:
  *   ref3d (B,N,3) fp32 world mm;  cams (B,V,MVG_CAM_FLOATS) fp32 packed cameras;
- *   vg (V*B, S, ld_vg) bf16, row r = v*B + b: columns [0,256) = value (rayconv output),
- *       [256,384) = sampling_offsets.weight @ feat, [384,448) = attention_weights.weight @ feat
- *       (both WITHOUT bias; bilinear interpolation commutes with the linear map);
+ *   value_hm (8 heads, V*B*S rows, 32) bf16, HEAD-MAJOR: head h of position s of map row r = v*B + b
+ *       is the 64 bytes at value_hm + h*value_head_stride + (r*S + s)*32 (rayconv output; the two
+ *       horizontal corners of a bilinear footprint are contiguous);
+ *   gmap (V*B*S rows, ld_g) bf16: columns [0,128) = sampling_offsets.weight @ feat, [128,192) =
+ *       attention_weights.weight @ feat (both WITHOUT bias; bilinear interpolation commutes with
+ *       the linear map).  Both are written by mvg_value_proj_gemm;
  *   qproj (B,N,192) fp32 = [sampling_offsets; attention_weights](tgt + query_pos) + bias.
  * Outputs:
  *   sampled (B,V,N,256) bf16 (input of output_proj), ref2d (B,V,N,2) fp32 normalised
@@ -139,12 +152,13 @@ typedef struct {
   int level_w[MVG_MAX_LEVELS];
   int level_start[MVG_MAX_LEVELS];
   int spatial_size;             /* S */
-  int ld_vg;                    /* row stride of vg in elements (>= 448) */
+  int ld_g;                     /* row stride of the offset/logit map G in elements (>= 192) */
   float img_w, img_h;           /* network image size (NETWORK.IMAGE_SIZE) */
+  int64_t value_head_stride;    /* elements between consecutive heads of value_hm (>= V*B*S*32) */
 } MvgSampleParams;
 
-MVG_API int mvg_project_sample_fused(const float* ref3d, const float* cams, const void* vg,
-                             const float* qproj, const MvgSampleParams* prm, void* sampled,
+MVG_API int mvg_project_sample_fused(const float* ref3d, const float* cams, const void* value_hm,
+                             const void* gmap, const float* qproj, const MvgSampleParams* prm, void* sampled,
                              float* ref2d, uint8_t* bounding, const float* refl_in,
                              void* workspace, void* stream);
 

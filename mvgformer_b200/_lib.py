@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("MVG_LIB_PATH", os.path.join(_HERE, "libmvg_b200.so"))
 MVG_F32, MVG_BF16 = 0, 1
 MVG_MAX_LEVELS = 4
 MVG_CAM_FLOATS = 64
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class MvgError(RuntimeError):
@@ -30,8 +30,8 @@ class MvgSampleParams(C.Structure):
                 ("num_levels", C.c_int),
                 ("level_h", C.c_int * MVG_MAX_LEVELS), ("level_w", C.c_int * MVG_MAX_LEVELS),
                 ("level_start", C.c_int * MVG_MAX_LEVELS),
-                ("spatial_size", C.c_int), ("ld_vg", C.c_int),
-                ("img_w", C.c_float), ("img_h", C.c_float)]
+                ("spatial_size", C.c_int), ("ld_g", C.c_int),
+                ("img_w", C.c_float), ("img_h", C.c_float), ("value_head_stride", C.c_int64)]
 
 
 _P = C.c_void_p
@@ -45,7 +45,8 @@ SIGNATURES = {
     "mvg_deform_backward": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "mvg_pyramid_to_channels_last": [_P, _I, _I, _P, _I, _I, _P, _P],
     "mvg_linear_bf16": [_P, _P, _P, _P, _I, _L, _I, _I, _L, _I, _P, _P],
-    "mvg_project_sample_fused": [_P, _P, _P, _P, C.POINTER(MvgSampleParams), _P, _P, _P, _P, _P, _P],
+    "mvg_project_sample_fused": [_P, _P, _P, _P, _P, C.POINTER(MvgSampleParams), _P, _P, _P, _P, _P, _P],
+    "mvg_value_proj_gemm": [_P, _P, _P, _L, _I, _P, _P, _P],
     "mvg_select_pad": [_P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "mvg_offsets_dlt": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P],
     "mvg_triangulate": [_P, _P, _P, _I, _I, _I, _P, _P],

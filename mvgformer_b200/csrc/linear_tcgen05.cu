@@ -40,7 +40,8 @@ template <typename OutT>
 __global__ void __launch_bounds__(kGemmThreadsV2, 1)
 linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_w,
-                         const __grid_constant__ CUtensorMap tmap_out, int use_tma_store,
+                         const __grid_constant__ CUtensorMap tmap_out,
+                         const __grid_constant__ CUtensorMap tmap_hm, int hm_period, int use_tma_store,
                          const float* __restrict__ bias,
                          const uint8_t* __restrict__ row_mask, OutT* __restrict__ out, int M, int N,
                          int K, int NC, int n_chunks, int groups, int64_t ldo, int relu) {
@@ -159,6 +160,15 @@ linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int u = u_begin; u < u_end; ++u) {
           const int c0 = u * kUnitCols;
           if (n0 + c0 >= N) break;                 // warp-uniform
+          // split mode (value / offset-logit projection of the pyramid): every hm_period units form
+          // one decoder layer's 448 columns; its first 4 units (8 heads x 32 channels) go to the
+          // head-major value tensor, the remaining 3 to the (rows, layers * 192) map G
+          int hm_head = -1, out_col = n0 + c0;
+          if (sizeof(OutT) == 2 && hm_period > 0) {
+            const int ug = (n0 + c0) / kUnitCols, layer = ug / hm_period, w = ug % hm_period;
+            if (w < 4) hm_head = layer * 8 + 2 * w;
+            else out_col = layer * (hm_period - 4) * kUnitCols + (w - 4) * kUnitCols;
+          }
           // the previous bulk store must have finished READING the staging tile
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
@@ -196,8 +206,13 @@ linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 uint4 o;
                 o.x = pack_bf16x2(v[8 * t], v[8 * t + 1]);     o.y = pack_bf16x2(v[8 * t + 2], v[8 * t + 3]);
                 o.z = pack_bf16x2(v[8 * t + 4], v[8 * t + 5]); o.w = pack_bf16x2(v[8 * t + 6], v[8 * t + 7]);
-                const int j = h * 4 + t;
-                *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = o;
+                if (hm_head >= 0) {
+                  // head-major value rows: one 32-row x 64-byte tile per head, SWIZZLE_64B
+                  *reinterpret_cast<uint4*>(stage + h * 2048 + lane * 64 + ((t ^ ((lane >> 1) & 3)) << 4)) = o;
+                } else {
+                  const int j = h * 4 + t;
+                  *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = o;
+                }
               }
             } else {
 #pragma unroll
@@ -210,7 +225,12 @@ linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a,
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmap_out, stage, n0 + c0, row0);
+            if (hm_head >= 0) {
+              tma_store_3d(&tmap_hm, stage, 0, row0, hm_head);
+              tma_store_3d(&tmap_hm, stage + 2048, 0, row0, hm_head + 1);
+            } else {
+              tma_store_2d(&tmap_out, stage, out_col, row0);
+            }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
@@ -314,10 +334,35 @@ static int make_out_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int co
   return MVG_OK;
 }
 
+// 3-D bf16 tensor (heads, rows, 32) for the head-major value store: box = (32 ch, 32 rows, 1 head),
+// 64-byte swizzle (matches the epilogue's per-head staging tiles).
+static int make_hm_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int heads) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return MVG_ELAUNCH;
+  }
+  const cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(heads)};
+  const cuuint64_t strides[2] = {64, static_cast<cuuint64_t>(rows) * 64};
+  const cuuint32_t box[3] = {32, 32, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(head-major) failed (%d) rows=%lld heads=%d", static_cast<int>(r),
+              static_cast<long long>(rows), heads);
+    return MVG_ELAUNCH;
+  }
+  return MVG_OK;
+}
+
+// `value_hm` != nullptr selects the split mode: `out` is then the G map (M, (Nout/448)*192) and the
+// value columns go to value_hm ((Nout/448)*8, M, 32).
 template <typename OutT>
 static int launch_linear(const void* A, const void* W, const float* bias, const uint8_t* row_mask,
                          void* out, int64_t M, int Nout, int K, int64_t ldo, int relu,
-                         cudaStream_t st) {
+                         cudaStream_t st, void* value_hm = nullptr) {
   // weight chunk width: as wide as fits 128 KB / one UMMA (256), split evenly over the chunks
   int nc_max = kMaxWBytes / (K * 2);
   nc_max = nc_max > 256 ? 256 : (nc_max / 16) * 16;
@@ -344,12 +389,22 @@ static int launch_linear(const void* A, const void* W, const float* bias, const 
   if (rc) return rc;
   rc = make_tmap(&tw, W, Nout, K, NC);
   if (rc) return rc;
-  CUtensorMap tout;
-  if (use_tma_store) {
+  CUtensorMap tout, thm;
+  int hm_period = 0;
+  if (value_hm != nullptr) {
+    hm_period = 7;                                   // 448 columns per layer = 7 units of 64
+    const int layers = Nout / 448;
+    rc = make_out_tmap(&tout, out, M, layers * 192, ldo, 2);
+    if (rc) return rc;
+    rc = make_hm_tmap(&thm, value_hm, M, layers * 8);
+    if (rc) return rc;
+  } else if (use_tma_store) {
     rc = make_out_tmap(&tout, out, M, Nout, ldo, static_cast<int>(sizeof(OutT)));
     if (rc) return rc;
+    thm = tout;  // unused by the kernel
   } else {
     tout = ta;   // unused by the kernel
+    thm = ta;
   }
   auto kern = linear_tcgen05_ws_kernel<OutT>;
   static bool attr_set = false;
@@ -362,7 +417,7 @@ static int launch_linear(const void* A, const void* W, const float* bias, const 
     attr_set = true;
   }
   kern<<<n_chunks * groups, kGemmThreadsV2, kSmemBytesV2, st>>>(
-      ta, tw, tout, use_tma_store, bias, row_mask, static_cast<OutT*>(out), static_cast<int>(M), Nout,
+      ta, tw, tout, thm, hm_period, use_tma_store, bias, row_mask, static_cast<OutT*>(out), static_cast<int>(M), Nout,
       K, NC, n_chunks, groups, ldo, relu);
   return check_launch("mvg_linear_bf16");
 }
@@ -393,4 +448,21 @@ extern "C" int mvg_linear_bf16(const void* A, const void* W, const float* bias, 
   }
   set_error("mvg_linear_bf16: unsupported out dtype %d", out_dtype);
   return MVG_EUNSUPPORTED;
+}
+
+
+extern "C" int mvg_value_proj_gemm(const void* feat, const void* W, const float* bias, int64_t M, int layers,
+                                   void* value_hm, void* gmap, void* stream) {
+  using namespace mvg;
+  MVG_REQUIRE(feat && W && value_hm && gmap, "mvg_value_proj_gemm: null pointer");
+  MVG_REQUIRE(M > 0 && M < (1ll << 31) && layers > 0 && layers * 448 <= 148 * 256,
+              "mvg_value_proj_gemm: bad shape (M=%lld layers=%d)", static_cast<long long>(M), layers);
+  const void* ptrs[] = {feat, W, value_hm, gmap};
+  for (const void* q : ptrs)
+    MVG_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0, "mvg_value_proj_gemm: operands must be 16-byte aligned");
+  MVG_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+              "mvg_value_proj_gemm: bias must be 16-byte aligned");
+  return launch_linear<__nv_bfloat16>(feat, W, bias, nullptr, gmap, M, layers * 448, 256,
+                                      static_cast<int64_t>(layers) * 192, 0, static_cast<cudaStream_t>(stream),
+                                      value_hm);
 }

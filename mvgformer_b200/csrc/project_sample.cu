@@ -49,7 +49,6 @@ constexpr int kWarps = MVG_PS_WARPS;   // warps per CTA; one persistent CTA per 
 constexpr int kPsUnroll = MVG_PS_UNROLL;
 constexpr int kQP = 192;           // 128 offset channels + 64 logit channels per level
 constexpr int kHeads = 8;
-constexpr int kVgValueCols = 256;  // value columns precede the G columns in a vg row
 constexpr int kPcThreads = 256;    // project_compact block
 
 // acc (two fp32 packed in a 64-bit register) += {w, w} * {bf16 lo, bf16 hi} of the 32-bit word u
@@ -184,14 +183,15 @@ project_compact_kernel(const float* __restrict__ ref3d, const MvgCamera* __restr
 // ------------------------------------------------------------------ gather
 template <int LV> struct WarpScratch {
   float proj[LV][kQP];                    // per pyramid level: Linear outputs (offsets | logits)
-  float4 cw[LV * 8 * kHeads];             // [sample][head]: 4 corner weights * attention
+  float4 cw[LV * 8 * kHeads];             // [sample][head]: weights * attention as {w00, w10, w01, w11}
+                                          // (block column dx = 0 pair, then dx = 1 pair)
   int base[LV * 8 * kHeads];              // [sample][head]: 16-byte offset of the clamped 2x2 block
 };
 
 template <int LV>
 __global__ void __launch_bounds__(kWarps * 32, 1)
-gather_kernel(const __nv_bfloat16* __restrict__ vg, const float* __restrict__ qproj,
-              const MvgSampleParams prm, __nv_bfloat16* __restrict__ sampled,
+gather_kernel(const __nv_bfloat16* __restrict__ value_hm, const __nv_bfloat16* __restrict__ gmap,
+              const float* __restrict__ qproj, const MvgSampleParams prm, __nv_bfloat16* __restrict__ sampled,
               const float* __restrict__ ref2d, const float* __restrict__ refl_in,
               const int* __restrict__ ws) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
@@ -199,19 +199,21 @@ gather_kernel(const __nv_bfloat16* __restrict__ vg, const float* __restrict__ qp
   const int warp = threadIdx.x >> 5;
   WarpScratch<LV>& sc = reinterpret_cast<WarpScratch<LV>*>(smem_dyn)[warp];
   const int N = prm.points, V = prm.views, B = prm.batch;
-  const int ld = prm.ld_vg;
-  const uint32_t ld16 = static_cast<uint32_t>(prm.ld_vg) >> 3;   // row stride in 16-byte units
+  const int ldg = prm.ld_g;            // row stride of the offset / logit map G, elements
   constexpr int NS = LV * 8;           // samples per head
   // phase-B ownership: head m = lane & 7, sample group sub = lane >> 3 (samples r = sub + 4 i):
   // a quarter-warp then stores 8 consecutive float4 slots [r][0..7] (conflict-free).
-  // phase-C ownership: head mc = lane >> 2, channel chunk subc = lane & 3 - the four lanes of a
-  // head read one 64-byte (texel, head) row with a single L1 request.
+  // phase-C ownership: lane = hsel * 8 + dx * 4 + chunk.  The value tensor is head-major
+  // ([head][row][32 ch], 64 B per (texel, head)), so the two horizontal corners of a bilinear
+  // footprint are 128 contiguous bytes: the 8 lanes (dx, chunk) of a quarter-warp fetch them with
+  // ONE L1 request, and one LDG.128 covers a block row of 4 heads (hsel).  Two passes (hg) cover
+  // the 8 heads, two loads (block rows dy) the footprint.
   const int m = lane & 7, sub = lane >> 3;
-  const int mc = lane >> 2, subc = lane & 3;
-  // identity B fragment of mma.m16n8k8: B[k][n] = (k == n), lane (g, t) holds k = 2t, 2t+1 of
-  // column n = g as a bf16 pair
-  const uint32_t b_ident = mc == 2 * subc ? 0x00003F80u : (mc == 2 * subc + 1 ? 0x3F800000u : 0u);
-
+  const int hsel = lane >> 3, dxl = (lane >> 2) & 1, subc = lane & 3;
+  // identity B fragment of mma.m16n8k8 (tensor-pipe unpack option): B[k][n] = (k == n), lane
+  // (g, t) = (lane >> 2, lane & 3) holds k = 2t, 2t+1 of column n = g as a bf16 pair
+  const uint32_t b_ident = (lane >> 2) == 2 * (lane & 3) ? 0x00003F80u
+                                                         : ((lane >> 2) == 2 * (lane & 3) + 1 ? 0x3F800000u : 0u);
   // One CTA owns one contiguous slice of the (compacted) item list; its 16 warps walk it
   // together (warp w: first + w, first + w + 16, ...), so at any moment one SM works on ~one
   // person's joints in one view and their overlapping sampling footprints share the SM's L1.
@@ -226,7 +228,8 @@ gather_kernel(const __nv_bfloat16* __restrict__ vg, const float* __restrict__ qp
     const int n = static_cast<int>(item % N);
     const int bv = static_cast<int>(item / N);
     const int v = bv % V, b = bv / V;
-    const __nv_bfloat16* vrow = vg + static_cast<int64_t>(v * B + b) * prm.spatial_size * ld;
+    const int64_t vrow0 = static_cast<int64_t>(v * B + b) * prm.spatial_size;     // first row of this view
+    const __nv_bfloat16* grow = gmap + vrow0 * ldg;
     float refl_x[LV], refl_y[LV];
     if (refl_in != nullptr) {          // ProjAttn.forward entry: reference points are given
 #pragma unroll
@@ -274,12 +277,11 @@ gather_kernel(const __nv_bfloat16* __restrict__ vg, const float* __restrict__ qp
         const bool oky0 = yy0 >= 0 && yy0 < H, oky1 = yy0 + 1 >= 0 && yy0 + 1 < H;
         const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
         const int ya = min(max(yy0, 0), H - 1), yb = min(max(yy0 + 1, 0), H - 1);
-        const __nv_bfloat16* gl = vrow + static_cast<int64_t>(prm.level_start[l]) * ld +
-                                  kVgValueCols + lane * 8;
-        cn[l][0] = ldg_nc_v4(gl + static_cast<int64_t>(ya * W + xa) * ld);
-        cn[l][1] = ldg_nc_v4(gl + static_cast<int64_t>(ya * W + xb) * ld);
-        cn[l][2] = ldg_nc_v4(gl + static_cast<int64_t>(yb * W + xa) * ld);
-        cn[l][3] = ldg_nc_v4(gl + static_cast<int64_t>(yb * W + xb) * ld);
+        const __nv_bfloat16* gl = grow + static_cast<int64_t>(prm.level_start[l]) * ldg + lane * 8;
+        cn[l][0] = ldg_nc_v4(gl + static_cast<int64_t>(ya * W + xa) * ldg);
+        cn[l][1] = ldg_nc_v4(gl + static_cast<int64_t>(ya * W + xb) * ldg);
+        cn[l][2] = ldg_nc_v4(gl + static_cast<int64_t>(yb * W + xa) * ldg);
+        cn[l][3] = ldg_nc_v4(gl + static_cast<int64_t>(yb * W + xb) * ldg);
         cwgt[l][0] = (oky0 && okx0) ? wn * ww : 0.f;
         cwgt[l][1] = (oky0 && okx1) ? wn * we : 0.f;
         cwgt[l][2] = (oky1 && okx0) ? ws * ww : 0.f;
@@ -354,58 +356,79 @@ gather_kernel(const __nv_bfloat16* __restrict__ vg, const float* __restrict__ qp
         const float rx0 = w_low < 0 ? lw : (w_low > W - 2 ? 0.f : hw);
         const float rx1 = w_low < 0 ? 0.f : (w_low > W - 2 ? hw : lw);
         const float sw = inside ? wgt : 0.f;
-        sc.cw[r * kHeads + m] = make_float4(ry0 * rx0 * sw, ry0 * rx1 * sw, ry1 * rx0 * sw, ry1 * rx1 * sw);
-        sc.base[r * kHeads + m] = (start + ha * W + wa) * static_cast<int>(ld16);
+        sc.cw[r * kHeads + m] = make_float4(ry0 * rx0 * sw, ry1 * rx0 * sw, ry0 * rx1 * sw, ry1 * rx1 * sw);
+        sc.base[r * kHeads + m] = (start + ha * W + wa) * 4;      // 16-byte units, 64 B per (texel, head)
       }
     }
     __syncwarp();
 
-    // ---------------- phase C (a5): gather 4 corners x NS samples, 8 channels per lane
-    uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};     // 8 fp32 accumulators as 4 packed pairs
-    const uint4* vlane16 = reinterpret_cast<const uint4*>(vrow + mc * 32 + subc * 8);
+    // ---------------- phase C (a5): gather 2 block rows x NS samples x 2 head groups
+    uint64_t acc2[2][4];                             // [head group][8 fp32 channels as 4 pairs]
+#pragma unroll
+    for (int hg = 0; hg < 2; ++hg) acc2[hg][0] = acc2[hg][1] = acc2[hg][2] = acc2[hg][3] = 0ull;
+    const uint4* vl[2];
+#pragma unroll
+    for (int hg = 0; hg < 2; ++hg)
+      vl[hg] = reinterpret_cast<const uint4*>(value_hm + (static_cast<int64_t>(hg * 4 + hsel) * prm.value_head_stride +
+                                                          vrow0 * 32)) + dxl * 4 + subc;
 #pragma unroll
     for (int l = 0; l < LV; ++l) {
-      const uint32_t rowstep16 = static_cast<uint32_t>(prm.level_w[l]) * ld16;
+      const uint32_t rowstep16 = static_cast<uint32_t>(prm.level_w[l]) * 4u;
 #pragma unroll kPsUnroll
       for (int p = 0; p < 8; ++p) {
         const int r = l * 8 + p;
-        const float4 cwv = sc.cw[r * kHeads + mc];
-        const uint4* p00 = vlane16 + static_cast<uint32_t>(sc.base[r * kHeads + mc]);
-        const uint4 c1 = __ldg(p00);
-        const uint4 c2 = __ldg(p00 + ld16);
-        const uint4 c3 = __ldg(p00 + rowstep16);
-        const uint4 c4 = __ldg(p00 + rowstep16 + ld16);
-        fma_corner(acc2, c1, cwv.x, b_ident);
-        fma_corner(acc2, c2, cwv.y, b_ident);
-        fma_corner(acc2, c3, cwv.z, b_ident);
-        fma_corner(acc2, c4, cwv.w, b_ident);
+#pragma unroll
+        for (int hg = 0; hg < 2; ++hg) {
+          // this lane's block column: (top, bottom) weights
+          const float2 cwv = reinterpret_cast<const float2*>(&sc.cw[r * kHeads + hg * 4 + hsel])[dxl];
+          const uint4* p0 = vl[hg] + static_cast<uint32_t>(sc.base[r * kHeads + hg * 4 + hsel]);
+          const uint4 ct = __ldg(p0);
+          const uint4 cb = __ldg(p0 + rowstep16);
+          fma_corner(acc2[hg], ct, cwv.x, b_ident);
+          fma_corner(acc2[hg], cb, cwv.y, b_ident);
+        }
       }
     }
+    // left + right block columns: lanes (dx = 0) and (dx = 1) hold the two halves of every sum;
+    // afterwards lane (hsel, dx, chunk) owns head 4 dx + hsel
     float acc[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) unpack2(acc2[i], acc[2 * i], acc[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) {
+      float a0, a1, b0, b1;
+      unpack2(acc2[0][i], a0, a1);
+      unpack2(acc2[1][i], b0, b1);
+      a0 += __shfl_xor_sync(0xffffffffu, a0, 4); a1 += __shfl_xor_sync(0xffffffffu, a1, 4);
+      b0 += __shfl_xor_sync(0xffffffffu, b0, 4); b1 += __shfl_xor_sync(0xffffffffu, b1, 4);
+      acc[2 * i] = dxl ? b0 : a0;
+      acc[2 * i + 1] = dxl ? b1 : a1;
+    }
     uint4 o;
     o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
     o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-    *reinterpret_cast<uint4*>(sampled + out_idx * 256 + lane * 8) = o;
+    *reinterpret_cast<uint4*>(sampled + out_idx * 256 + (dxl * 4 + hsel) * 32 + subc * 8) = o;
     __syncwarp();   // scratch is reused by the next item
   }
 }
 
 }  // namespace mvg
 
-extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, const void* vg,
-                                        const float* qproj, const MvgSampleParams* prm,
+extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, const void* value_hm,
+                                        const void* gmap, const float* qproj, const MvgSampleParams* prm,
                                         void* sampled, float* ref2d, uint8_t* bounding,
                                         const float* refl_in, void* workspace, void* stream) {
   using namespace mvg;
-  MVG_REQUIRE(vg && qproj && prm && sampled, "mvg_project_sample_fused: null pointer");
+  MVG_REQUIRE(value_hm && gmap && qproj && prm && sampled, "mvg_project_sample_fused: null pointer");
+  MVG_REQUIRE((reinterpret_cast<uintptr_t>(value_hm) & 15) == 0 && (reinterpret_cast<uintptr_t>(gmap) & 15) == 0,
+              "mvg_project_sample_fused: value / G map must be 16-byte aligned");
   MVG_REQUIRE(refl_in || (ref3d && cams && ref2d && bounding && workspace),
               "mvg_project_sample_fused: projection inputs/outputs/workspace missing");
   MVG_REQUIRE(prm->num_levels >= 1 && prm->num_levels <= MVG_MAX_LEVELS,
               "mvg_project_sample_fused: num_levels %d out of range", prm->num_levels);
   MVG_REQUIRE(prm->batch > 0 && prm->views > 0 && prm->points > 0, "mvg_project_sample_fused: empty shape");
-  MVG_REQUIRE(prm->ld_vg >= 448 && prm->ld_vg % 8 == 0, "mvg_project_sample_fused: ld_vg %d", prm->ld_vg);
+  MVG_REQUIRE(prm->ld_g >= 192 && prm->ld_g % 8 == 0, "mvg_project_sample_fused: ld_g %d", prm->ld_g);
+  MVG_REQUIRE(prm->value_head_stride >= static_cast<int64_t>(prm->batch) * prm->views * prm->spatial_size * 32 &&
+                  prm->value_head_stride % 8 == 0,
+              "mvg_project_sample_fused: value_head_stride %lld", static_cast<long long>(prm->value_head_stride));
   int s = 0;
   for (int l = 0; l < prm->num_levels; ++l) {
     MVG_REQUIRE(prm->level_h[l] > 1 && prm->level_w[l] > 1 && prm->level_start[l] == s,
@@ -414,7 +437,7 @@ extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, c
   }
   MVG_REQUIRE(s == prm->spatial_size, "mvg_project_sample_fused: spatial_size %d != sum H*W %d",
               prm->spatial_size, s);
-  MVG_REQUIRE(static_cast<int64_t>(s) * (prm->ld_vg / 8) < (1ll << 31),
+  MVG_REQUIRE(static_cast<int64_t>(s) * 4 < (1ll << 31),
               "mvg_project_sample_fused: per-view map too large for 32-bit texel offsets");
   const int64_t total = static_cast<int64_t>(prm->batch) * prm->views * prm->points;
   MVG_REQUIRE(total < (1ll << 31), "mvg_project_sample_fused: too many items");
@@ -423,7 +446,8 @@ extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, c
   const int grid = static_cast<int>(want < kNumSMs ? (want < 1 ? 1 : want) : kNumSMs);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const MvgCamera* cam = reinterpret_cast<const MvgCamera*>(cams);
-  const __nv_bfloat16* vgp = static_cast<const __nv_bfloat16*>(vg);
+  const __nv_bfloat16* vhm = static_cast<const __nv_bfloat16*>(value_hm);
+  const __nv_bfloat16* gmp = static_cast<const __nv_bfloat16*>(gmap);
   __nv_bfloat16* sp = static_cast<__nv_bfloat16*>(sampled);
   int* ws = refl_in ? nullptr : static_cast<int*>(workspace);
   if (ws != nullptr) {
@@ -450,7 +474,7 @@ extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, c
       }                                                                                         \
       attr_done = true;                                                                         \
     }                                                                                           \
-    gather_kernel<LV><<<grid, kWarps * 32, smem, st>>>(vgp, qproj, *prm, sp, ref2d, refl_in, ws); \
+    gather_kernel<LV><<<grid, kWarps * 32, smem, st>>>(vhm, gmp, qproj, *prm, sp, ref2d, refl_in, ws); \
   }
   switch (prm->num_levels) {
     case 1: MVG_LAUNCH_PS(1) break;

@@ -10,7 +10,7 @@ init_self_attention=False, open_forward_ffn=True, bayesian_update=False,
 triangulation_method in {'linalg','batch'}; anything else raises NotImplementedError.
 
 One layer = the following device work (no host synchronisation anywhere):
-  1. vg     = pyramid @ [rayconv; sampling_offsets; attention_weights]^T   tensor cores
+  1. value_hm | G = pyramid @ [rayconv; sampling_offsets; attention_weights]^T   tensor cores
      (hoisted into DQDecoder.forward: one GEMM for all L layers, the pyramid is read once)
   2. qproj  = (tgt + query_pos) @ [sampling_offsets; attention_weights]^T + b
   3. mvg_project_sample_fused: projection + offsets/softmax + deformable gather (a3-a5)
@@ -106,13 +106,16 @@ class DecoderContext:
                 layers[0]._vg_cat_cache = cached
             w_all, b_all = cached[1], cached[2]
         with prof.stage("vg_gemm"):
-            self.vg_all = linear(feat_cl, w_all, b_all)                      # (V*B,S,448*Ld)
-        self.ld_vg = self.vg_all.shape[-1]
+            # value (head-major) + offset/logit map G for all distinct layers, one GEMM
+            self.value_hm, self.gmap = ops.value_proj(feat_cl, w_all, b_all, len(distinct))
+        self.ld_g = self.gmap.shape[-1]
+        self.value_head_stride = self.value_hm.stride(0)
         self._slot = {id(l): i for i, l in enumerate(distinct)}
 
-    def vg_for(self, layer: "DQDecoderLayer") -> torch.Tensor:
+    def vg_for(self, layer: "DQDecoderLayer"):
+        """-> (the layer's 8 heads of value_hm, its 192-column slice of G)."""
         i = self._slot[id(layer)]
-        return self.vg_all[..., i * 448:]
+        return self.value_hm[i * 8:(i + 1) * 8], self.gmap[:, i * 192:]
 
 
 class DQDecoderLayer(nn.Module):
@@ -233,10 +236,10 @@ class DQDecoderLayer(nn.Module):
             q_bf = ops.add_cast_bf16(tgt, qp)                                    # with_pos_embed
             qproj = linear(q_bf, pw["w_q"], pw["b_q"], out_dtype=torch.float32)  # (B,N,192)
         # 3. fused projection + sampling
-        vg = ctx.vg_for(self)
-        prm = ops.make_sample_params(B, V, N, ctx.levels, ctx.ld_vg, ctx.img_size)
+        value_hm, gmap = ctx.vg_for(self)
+        prm = ops.make_sample_params(B, V, N, ctx.levels, ctx.ld_g, ctx.img_size, ctx.value_head_stride)
         with prof.stage("project_sample_fused"):
-            sampled, ref2d, bounding = ops.project_sample_fused(ref3d, ctx.cams, vg, qproj, prm)
+            sampled, ref2d, bounding = ops.project_sample_fused(ref3d, ctx.cams, value_hm, gmap, qproj, prm)
         prof.note("inview_items", ops._last_work[0])       # no-op unless profiling is enabled
         # 4. output_proj, mask, view-mean, update MLP, LN, FFN, LN
         with prof.stage("output_proj"):

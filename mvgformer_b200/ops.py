@@ -73,8 +73,35 @@ def linear_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
 _last_work: Optional[torch.Tensor] = None
 
 
+def value_proj(feat_cl: torch.Tensor, w_all: torch.Tensor, b_all: Optional[torch.Tensor], layers: int):
+    """The pyramid projections of `layers` decoder layers in one GEMM, in the gather's layouts.
+    feat_cl (rows, S, 256) bf16; w_all (layers*448, 256) bf16 = per layer [rayconv | sampling_offsets |
+    attention_weights]; b_all (layers*448) fp32.  -> value_hm (layers*8, rows*S, 32) bf16 head-major,
+    gmap (rows*S, layers*192) bf16."""
+    from .linear import get_backend
+    M = feat_cl.shape[0] * feat_cl.shape[1]
+    dev = feat_cl.device
+    if get_backend() != "tcgen05":
+        # library A/B path (cuBLASLt through torch): same contraction, layouts rebuilt with torch ops
+        y = torch.mm(feat_cl.reshape(M, 256), w_all.t(), out_dtype=torch.float32)
+        if b_all is not None:
+            y = y + b_all
+        y = y.to(torch.bfloat16).view(M, layers, 448)
+        value_hm = y[:, :, :256].reshape(M, layers * 8, 32).permute(1, 0, 2).contiguous()
+        return value_hm, y[:, :, 256:].reshape(M, layers * 192).contiguous()
+    lib = _lib.load()
+    value_hm = torch.empty((layers * 8, M, 32), dtype=torch.bfloat16, device=dev)
+    gmap = torch.empty((M, layers * 192), dtype=torch.bfloat16, device=dev)
+    check(lib.mvg_value_proj_gemm(feat_cl.data_ptr(), w_all.data_ptr(), _lib.ptr(b_all), M, layers,
+                                  value_hm.data_ptr(), gmap.data_ptr(), stream_ptr(dev)), "mvg_value_proj_gemm")
+    return value_hm, gmap
+
+
+_last_work: Optional[torch.Tensor] = None
+
+
 def make_sample_params(batch: int, views: int, points: int, levels: Sequence[Tuple[int, int]],
-                       ld_vg: int, img_size: Sequence[float]) -> MvgSampleParams:
+                       ld_g: int, img_size: Sequence[float], value_head_stride: int) -> MvgSampleParams:
     prm = MvgSampleParams()
     prm.batch, prm.views, prm.points = batch, views, points
     prm.num_levels = len(levels)
@@ -83,24 +110,27 @@ def make_sample_params(batch: int, views: int, points: int, levels: Sequence[Tup
         prm.level_h[i], prm.level_w[i], prm.level_start[i] = int(h), int(w), start
         start += int(h) * int(w)
     prm.spatial_size = start
-    prm.ld_vg = int(ld_vg)
+    prm.ld_g = int(ld_g)
     prm.img_w, prm.img_h = float(img_size[0]), float(img_size[1])
+    prm.value_head_stride = int(value_head_stride)
     return prm
 
 
 def project_sample_fused(ref3d: Optional[torch.Tensor], cams: Optional[torch.Tensor],
-                         vg: torch.Tensor, qproj: torch.Tensor, prm: MvgSampleParams,
-                         refl: Optional[torch.Tensor] = None):
-    """-> sampled (B,V,N,256) bf16, ref2d (B,V,N,2) fp32, bounding (B,V,N) uint8."""
+                         value_hm: torch.Tensor, gmap: torch.Tensor, qproj: torch.Tensor,
+                         prm: MvgSampleParams, refl: Optional[torch.Tensor] = None):
+    """value_hm: this layer's 8 heads of the head-major value tensor (8, rows*S, 32); gmap: this
+    layer's 192 columns of G (a column slice, row stride prm.ld_g).
+    -> sampled (B,V,N,256) bf16, ref2d (B,V,N,2) fp32, bounding (B,V,N) uint8."""
     lib = _lib.load()
-    dev = vg.device
+    dev = value_hm.device
     B, V, N = prm.batch, prm.views, prm.points
     sampled = torch.empty((B, V, N, 256), dtype=torch.bfloat16, device=dev)
     ref2d = torch.empty((B, V, N, 2), dtype=torch.float32, device=dev)
     bounding = torch.empty((B, V, N), dtype=torch.uint8, device=dev)
     # in-view item list (count + indices); not needed on the ProjAttn entry (refl given)
     work = None if refl is not None else torch.empty((B * V * N + 4,), dtype=torch.int32, device=dev)
-    check(lib.mvg_project_sample_fused(_lib.ptr(ref3d), _lib.ptr(cams), vg.data_ptr(),
+    check(lib.mvg_project_sample_fused(_lib.ptr(ref3d), _lib.ptr(cams), value_hm.data_ptr(), gmap.data_ptr(),
                                        qproj.data_ptr(), C.byref(prm), sampled.data_ptr(),
                                        ref2d.data_ptr(), bounding.data_ptr(), _lib.ptr(refl),
                                        _lib.ptr(work), stream_ptr(dev)), "mvg_project_sample_fused")

@@ -134,10 +134,10 @@ class ProjAttn(nn.Module):
             if not torch.cuda.is_current_stream_capturing() else True
         w = self.packed_weights()
         feat_cl = ops.pyramid_to_channels_last(src_views)                       # (n_views,S,256)
-        vg = linear(feat_cl, w["w_vg"], w["b_vg"])                              # (n_views,S,448)
+        value_hm, gmap = ops.value_proj(feat_cl, w["w_vg"], w["b_vg"], 1)       # head-major value | G
         qproj = linear(query.to(torch.bfloat16), w["w_q"], w["b_q"], out_dtype=torch.float32)
-        prm = ops.make_sample_params(n_views, 1, Lq, levels, vg.shape[-1], (1.0, 1.0))
+        prm = ops.make_sample_params(n_views, 1, Lq, levels, gmap.shape[-1], (1.0, 1.0), value_hm.stride(0))
         refl = reference_points.float().contiguous()
-        sampled, _, _ = ops.project_sample_fused(None, None, vg, qproj, prm, refl=refl)
+        sampled, _, _ = ops.project_sample_fused(None, None, value_hm, gmap, qproj, prm, refl=refl)
         out = linear(sampled.view(n_views, Lq, 256), w["w_o"], w["b_o"], out_dtype=torch.float32)
         return out

@@ -49,16 +49,16 @@ with torch.no_grad():
     N = Q * J
     q_bf = ops.add_cast_bf16(tgt.float().contiguous(), qpos.float().contiguous())
     qproj = linear(q_bf, pw["w_q"], pw["b_q"], out_dtype=torch.float32)
-    vg = ctx.vg_for(lyr)
-    prm = ops.make_sample_params(B, V, N, ctx.levels, ctx.ld_vg, ctx.img_size)
+    value_hm, gmap = ctx.vg_for(lyr)
+    prm = ops.make_sample_params(B, V, N, ctx.levels, ctx.ld_g, ctx.img_size, ctx.value_head_stride)
     ref3d = ref.reshape(B, N, 3).float().contiguous()
     for _ in range(3):
-        sampled, ref2d, bounding = ops.project_sample_fused(ref3d, ctx.cams, vg, qproj, prm)
+        sampled, ref2d, bounding = ops.project_sample_fused(ref3d, ctx.cams, value_hm, gmap, qproj, prm)
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(a.iters):
-        sampled, ref2d, bounding = ops.project_sample_fused(ref3d, ctx.cams, vg, qproj, prm)
+        sampled, ref2d, bounding = ops.project_sample_fused(ref3d, ctx.cams, value_hm, gmap, qproj, prm)
     e.record()
     torch.cuda.synchronize()
     us = s.elapsed_time(e) * 1e3 / a.iters
