@@ -142,8 +142,8 @@ MVG_API int mvg_value_proj_gemm(const void* feat, const void* W, const float* bi
  *   (ref3d, cams, ref2d, bounding, workspace may then be NULL).
  * Out-of-view points (bounding == 0): the reference multiplies their attention feature by 0
  *   (dq_decoder.py:585-586) and reads it nowhere else, so they are not gathered; their
- *   `sampled` rows are zeros.  `workspace` (device, 4 * (B*V*N + 4) bytes, contents
- *   irrelevant on entry) receives the count and the list of in-view items.
+ *   `sampled` rows are zeros.  `workspace` (device, 4 * (B*V*N + B*V + 4) bytes, contents
+ *   irrelevant on entry) receives, per (frame, view), the count and the list of in-view items.
  */
 typedef struct {
   int batch, views, points;     /* B, V, N */

@@ -105,8 +105,10 @@ __device__ __forceinline__ void fma_corner(uint64_t (&acc)[4], const uint4& c, f
 }
 
 // ------------------------------------------------------------------ projection + compaction
-// ws[0] = number of in-view items (zeroed by the host wrapper before the launch),
-// ws[4 ...] = their flat indices (b*V + v)*N + n, ordered inside each 256-item block.
+// One block = 256 consecutive points of ONE (frame, view) pair bv = blockIdx.y.
+// ws[bv] = number of in-view points of that pair (zeroed by the host wrapper before the launch),
+// ws[hdr + bv*N ...] = their flat item indices bv*N + n, ordered inside each 256-point block
+// (hdr = B*V rounded up to a multiple of 4).
 __global__ void __launch_bounds__(kPcThreads)
 project_compact_kernel(const float* __restrict__ ref3d, const MvgCamera* __restrict__ cams,
                        const MvgSampleParams prm, float* __restrict__ ref2d_out,
@@ -115,13 +117,12 @@ project_compact_kernel(const float* __restrict__ ref3d, const MvgCamera* __restr
   __shared__ int warp_cnt[kPcThreads / 32];
   __shared__ int block_base;
   const int N = prm.points, V = prm.views;
-  const int64_t total = static_cast<int64_t>(prm.batch) * V * N;
-  const int64_t item = static_cast<int64_t>(blockIdx.x) * kPcThreads + threadIdx.x;
+  const int bv = blockIdx.y;
+  const int n = blockIdx.x * kPcThreads + threadIdx.x;
+  const int64_t item = static_cast<int64_t>(bv) * N + n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   bool inb = false;
-  if (item < total) {
-    const int n = static_cast<int>(item % N);
-    const int bv = static_cast<int>(item / N);
+  if (n < N) {
     const int b = bv / V;
     const MvgCamera* cam = cams + bv;   // (B,V) row-major == item / N
     const float* x3 = ref3d + (static_cast<int64_t>(b) * N + n) * 3;
@@ -154,7 +155,7 @@ project_compact_kernel(const float* __restrict__ ref3d, const MvgCamera* __restr
   }
   const uint32_t in_mask = __ballot_sync(0xffffffffu, inb);
   // out-of-view rows of `sampled` are defined (zeros); a warp writes one 512-byte row at a time
-  uint32_t out_mask = __ballot_sync(0xffffffffu, item < total && !inb);
+  uint32_t out_mask = __ballot_sync(0xffffffffu, n < N && !inb);
   const int64_t item0 = item - lane;
   while (out_mask) {
     const int src = __ffs(out_mask) - 1;
@@ -171,12 +172,13 @@ project_compact_kernel(const float* __restrict__ ref3d, const MvgCamera* __restr
       warp_cnt[w] = s;
       s += c;
     }
-    block_base = s > 0 ? atomicAdd(ws, s) : 0;
+    block_base = s > 0 ? atomicAdd(ws + bv, s) : 0;
   }
   __syncthreads();
   if (inb) {
     const int pos = block_base + warp_cnt[warp] + __popc(in_mask & ((1u << lane) - 1u));
-    ws[4 + pos] = static_cast<int>(item);
+    const int hdr = (prm.batch * V + 3) & ~3;
+    ws[hdr + static_cast<int64_t>(bv) * N + pos] = static_cast<int>(item);
   }
 }
 
@@ -214,16 +216,22 @@ gather_kernel(const __nv_bfloat16* __restrict__ value_hm, const __nv_bfloat16* _
   // (g, t) = (lane >> 2, lane & 3) holds k = 2t, 2t+1 of column n = g as a bf16 pair
   const uint32_t b_ident = (lane >> 2) == 2 * (lane & 3) ? 0x00003F80u
                                                          : ((lane >> 2) == 2 * (lane & 3) + 1 ? 0x3F800000u : 0u);
-  // One CTA owns one contiguous slice of the (compacted) item list; its 16 warps walk it
-  // together (warp w: first + w, first + w + 16, ...), so at any moment one SM works on ~one
-  // person's joints in one view and their overlapping sampling footprints share the SM's L1.
-  const int64_t total = ws != nullptr ? static_cast<int64_t>(__ldg(ws))
-                                      : static_cast<int64_t>(B) * V * N;
-  const int64_t first = total * blockIdx.x / gridDim.x;
-  const int64_t last = total * (blockIdx.x + 1) / gridDim.x;
+  // View-major sweep: for every (frame, view) pair in turn, each CTA takes an equal slice of that
+  // pair's in-view list and its 16 warps walk it together (warp w: first + w, first + w + 16, ...).
+  // All SMs therefore read ONE view's value / G maps at a time (36 MB, L2-resident) instead of all
+  // views at once (180 MB > 126 MB L2), and inside a slice an SM still works on ~one person's
+  // joints, whose overlapping footprints share its L1.
+  const int BV = B * V;
+  const int hdr = (BV + 3) & ~3;
 #pragma unroll 1
-  for (int64_t idx = first + warp; idx < last; idx += kWarps) {
-    const int64_t item = ws != nullptr ? static_cast<int64_t>(__ldg(ws + 4 + idx)) : idx;
+  for (int bvi = 0; bvi < BV; ++bvi) {
+  const int cnt = ws != nullptr ? __ldg(ws + bvi) : N;
+  const int first = static_cast<int>(static_cast<int64_t>(cnt) * blockIdx.x / gridDim.x);
+  const int last = static_cast<int>(static_cast<int64_t>(cnt) * (blockIdx.x + 1) / gridDim.x);
+#pragma unroll 1
+  for (int idx = first + warp; idx < last; idx += kWarps) {
+    const int64_t item = ws != nullptr ? static_cast<int64_t>(__ldg(ws + hdr + static_cast<int64_t>(bvi) * N + idx))
+                                       : static_cast<int64_t>(bvi) * N + idx;
     const int64_t out_idx = item;
     const int n = static_cast<int>(item % N);
     const int bv = static_cast<int>(item / N);
@@ -408,6 +416,7 @@ gather_kernel(const __nv_bfloat16* __restrict__ value_hm, const __nv_bfloat16* _
     *reinterpret_cast<uint4*>(sampled + out_idx * 256 + (dxl * 4 + hsel) * 32 + subc * 8) = o;
     __syncwarp();   // scratch is reused by the next item
   }
+  }
 }
 
 }  // namespace mvg
@@ -451,12 +460,13 @@ extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, c
   __nv_bfloat16* sp = static_cast<__nv_bfloat16*>(sampled);
   int* ws = refl_in ? nullptr : static_cast<int*>(workspace);
   if (ws != nullptr) {
-    cudaError_t e = cudaMemsetAsync(ws, 0, 16, st);
+    const int hdr = (prm->batch * prm->views + 3) & ~3;
+    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(int) * hdr, st);
     if (e != cudaSuccess) {
       set_error("mvg_project_sample_fused: cudaMemsetAsync: %s", cudaGetErrorString(e));
       return MVG_ELAUNCH;
     }
-    const int pc_grid = static_cast<int>((total + kPcThreads - 1) / kPcThreads);
+    const dim3 pc_grid((prm->points + kPcThreads - 1) / kPcThreads, prm->batch * prm->views);
     project_compact_kernel<<<pc_grid, kPcThreads, 0, st>>>(ref3d, cam, *prm, ref2d, bounding, sp, ws);
     int rc = check_launch("mvg_project_sample_fused(project_compact)");
     if (rc != MVG_OK) return rc;

@@ -240,7 +240,7 @@ class DQDecoderLayer(nn.Module):
         prm = ops.make_sample_params(B, V, N, ctx.levels, ctx.ld_g, ctx.img_size, ctx.value_head_stride)
         with prof.stage("project_sample_fused"):
             sampled, ref2d, bounding = ops.project_sample_fused(ref3d, ctx.cams, value_hm, gmap, qproj, prm)
-        prof.note("inview_items", ops._last_work[0])       # no-op unless profiling is enabled
+        prof.note("inview_items", ops._last_work[:B * V].sum())   # no-op unless profiling is enabled
         # 4. output_proj, mask, view-mean, update MLP, LN, FFN, LN
         with prof.stage("output_proj"):
             # (B,V,N,256) bf16, rows of out-of-view points zeroed in the epilogue (:585-586)

@@ -128,14 +128,14 @@ def project_sample_fused(ref3d: Optional[torch.Tensor], cams: Optional[torch.Ten
     sampled = torch.empty((B, V, N, 256), dtype=torch.bfloat16, device=dev)
     ref2d = torch.empty((B, V, N, 2), dtype=torch.float32, device=dev)
     bounding = torch.empty((B, V, N), dtype=torch.uint8, device=dev)
-    # in-view item list (count + indices); not needed on the ProjAttn entry (refl given)
-    work = None if refl is not None else torch.empty((B * V * N + 4,), dtype=torch.int32, device=dev)
+    # per-(frame, view) in-view counts + item lists; not needed on the ProjAttn entry (refl given)
+    work = None if refl is not None else torch.empty((B * V * N + B * V + 4,), dtype=torch.int32, device=dev)
     check(lib.mvg_project_sample_fused(_lib.ptr(ref3d), _lib.ptr(cams), value_hm.data_ptr(), gmap.data_ptr(),
                                        qproj.data_ptr(), C.byref(prm), sampled.data_ptr(),
                                        ref2d.data_ptr(), bounding.data_ptr(), _lib.ptr(refl),
                                        _lib.ptr(work), stream_ptr(dev)), "mvg_project_sample_fused")
     global _last_work
-    _last_work = work          # diagnostics only (profiling.note in dq_decoder): [0] = in-view items
+    _last_work = work          # diagnostics only (profiling.note in dq_decoder): [:B*V] = in-view counts
     return sampled, ref2d, bounding
 
 

@@ -41,7 +41,7 @@ def note(name: str, value: torch.Tensor) -> None:
     """Keeps a (cloned) device scalar for later inspection, e.g. the number of in-view items the
     gather processed; no synchronisation happens here."""
     if _enabled:
-        _notes[name].append(value.detach().clone())
+        _notes[name].append(value.detach().clone() if callable(getattr(value, "detach", None)) else value)
 
 
 def notes() -> Dict[str, List[float]]:

@@ -10,7 +10,9 @@ cat gpurun_out/bench_$tag.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 400 --csv \
   --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-graph \
   > gpurun_out/launches_$tag.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gather_kernel|project_compact|linear_tcgen05|ffn_chain|offsets_dlt|pyramid_to_cl|select_pad|class_head|masked_view_mean|add_cast" -s 162 -c 54 -o gpurun_out/step_$tag \
+# one decoder layer + the per-call kernels (pyramid hand-off, value GEMM): 15 launches, ~40 replays each.
+# Keep the report small: gpurun merges at most 64 MiB back.
+timeout 600 ncu --set full --clock-control none -k regex:"gather_kernel|project_compact|linear_tcgen05|ffn_chain|offsets_dlt|pyramid_to_cl|select_pad|class_head|masked_view_mean|add_cast" -s 162 -c 15 -o gpurun_out/step_$tag \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-graph > gpurun_out/step_$tag.log 2>&1
 tail -2 gpurun_out/step_$tag.log | cut -c1-200
 ls -la gpurun_out/
