@@ -482,7 +482,14 @@ def run_ours(a):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # dist.destroy_process_group() dead-locks while CUDA graphs that captured NCCL work are still
+        # alive (observed on 2 x B200: the JSON line is out, the call never returns).  All ranks
+        # rendezvous, flush and leave without tearing the communicator down.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
