@@ -95,3 +95,45 @@ def test_weight_packing_layout():
     with torch.no_grad():
         pa.rayconv.weight.mul_(2.0)
     assert pa.packed_weights() is not pk                  # invalidated by the in-place update
+
+
+def test_pre_post_and_packed_pyramid_host_behaviour():
+    """Host mirrors of the section-8f steps: no CPU fallback, reference-style argument checks,
+    unsupported configuration branches raise, state_dict keys match the reference's names."""
+    from mvgformer_b200 import ops, postprocess as post
+    qi = mvg.QueryInit(20, 15, 256, syn.PANOPTIC["space_size"], syn.PANOPTIC["space_center"])
+    assert set(qi.state_dict()) == {"joint_embedding.weight", "instance_embedding.weight"}   # dq_transformer.py:161-167
+    assert qi._lin.numel() == 5                              # ceil(sqrt(20)) roots per axis (:301)
+    assert np.array_equal(qi.t_pose_origin.numpy(), syn.TPOSE_MM)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        qi(2)
+    for kw in (dict(query_embed_type="per_joint"), dict(init_ref_method="gt_noise"), dict(close_pose_embedding=True)):
+        with pytest.raises(NotImplementedError):
+            mvg.QueryInit(20, 15, 256, [1, 1, 1], [0, 0, 0], **kw)
+    with pytest.raises(ValueError):
+        mvg.QueryInit(20, 15, 256, [1, 1, 1], [0, 0, 0], t_pose=np.zeros((14, 3)))
+    with pytest.raises(_lib.MvgError, match="Not implemented on the CPU"):
+        post.assemble_predictions(torch.zeros(1, 30, 3), torch.zeros(1, 2, 2), 0.3)
+    with pytest.raises(_lib.MvgError, match="Not implemented on the CPU"):
+        post.nearby_joints_nms(torch.zeros(1, 2, 15, 5), torch.zeros(1, 2, dtype=torch.int32),
+                               torch.zeros(1, dtype=torch.int32))
+    with pytest.raises(_lib.MvgError):
+        ops.PackedPyramid(torch.zeros(2, 48, 256, dtype=torch.bfloat16), [(4, 4)] * 3)       # CPU tensor
+    with pytest.raises(_lib.MvgError):
+        ops.PackedPyramid(torch.zeros(2, 48, 256), [(4, 4)] * 3)                             # not bf16
+
+
+def test_sample_params_struct_matches_header():
+    """ctypes mirror of MvgSampleParams: field order / types as declared in include/mvg_b200.h."""
+    text = open(os.path.join(ROOT, "include", "mvg_b200.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} MvgSampleParams;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(",")[0:]:
+            names.append(re.sub(r"\[.*?\]", "", part.split()[-1]).strip())
+    assert names == [n for n, _ in _lib.MvgSampleParams._fields_], (names, _lib.MvgSampleParams._fields_)
+    assert ctypes.sizeof(_lib.MvgSampleParams) == 4 * 20 + 8
