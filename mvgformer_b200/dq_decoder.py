@@ -71,7 +71,7 @@ def _get_clones(module, N):
 
 class DecoderContext:
     """Per-call device state shared by all layers: channels-last pyramid, packed cameras,
-    the pre-projected value/offset/logit map `vg` and static shape info."""
+    the pre-projected head-major value tensor + offset/logit map G and static shape info."""
 
     def __init__(self, src_views: Sequence[torch.Tensor], meta: List[Dict], img_size,
                  layers: Sequence["DQDecoderLayer"], batch_size: int):

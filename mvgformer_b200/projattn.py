@@ -6,7 +6,7 @@ signature.  Only the configuration the shipped model uses is implemented -
 branches raise NotImplementedError (no silent fallback).
 
 Forward = 3 dense projections on tensor cores + ONE fused gather kernel:
-  vg    = feat_cl @ [rayconv; sampling_offsets; attention_weights]^T      (S x 448 per view)
+  value_hm | G = feat_cl @ [rayconv; sampling_offsets; attention_weights]^T  (head-major value, S x 192 map)
   qproj = query   @ [sampling_offsets; attention_weights]^T + bias        (N x 192)
   sampled = mvg_project_sample_fused(...)                                 (csrc/project_sample.cu)
   out   = sampled @ output_proj^T + bias
