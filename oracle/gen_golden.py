@@ -17,6 +17,7 @@ Fixtures (all produced by reference code, file:line given per entry):
   triangulate.npz     multiview.triangulate_batch_of_points_batch_version
                       (lib/mvn/utils/multiview.py:257-269), fp32 (as shipped) and the same
                       reference code fed float64 inputs (its exact-arithmetic answer)
+  decoder_configs.npz one DQDecoderLayer.forward on the 7-view / Shelf / multi-frame shapes (BASELINE configs[2..4])
   pre_post.npz        sample_space reference points (lib/models/dq_transformer.py:298-323),
                       nearby_joints_nms keep lists (lib/core/nms.py:210-284), inverse_sigmoid
   state_dict_keys.json  parameter names/shapes of the reference DQDecoder
@@ -180,6 +181,35 @@ def gen_triangulate():
     np.savez_compressed(os.path.join(GOLD, "triangulate.npz"), **out)
 
 
+OTHER_CONFIGS = (("panoptic_v7", "PANOPTIC", 7, 1, 6, ((20, 36), (10, 18), (5, 9))),      # BASELINE configs[3]
+                 ("shelf_v5", "SHELF", 5, 2, 5, ((19, 25), (10, 13), (5, 7))),            # BASELINE configs[4]
+                 ("panoptic_b4", "PANOPTIC", 5, 4, 3, ((20, 36), (10, 18), (5, 9))))       # configs[2]: frames per call
+
+
+def other_config_scene(cfg_name, V, B, Q, levels, seed=31):
+    sc = syn.make_scene(getattr(syn, cfg_name), batch=B, n_views=V, num_instance=Q, seed=seed, levels=levels)
+    sd = syn.make_decoder_state_dict(1, np.random.default_rng(17), offset_px=1.0)
+    return sc, sd
+
+
+def gen_decoder_other_configs():
+    """tests/golden/decoder_configs.npz: one reference DQDecoderLayer.forward
+    (lib/models/dq_decoder.py:850-1045) on the shapes of BASELINE.json configs[2..4] - 7 views, the Shelf
+    image / network sizes, several frames per call - so that the oracle is pinned there too."""
+    out = {}
+    for tag, cfg_name, V, B, Q, levels in OTHER_CONFIGS:
+        sc, sd = other_config_scene(cfg_name, V, B, Q, levels)
+        dec = build_reference_decoder(sc, sd, 1)
+        masks = [torch.zeros(f.shape[0], f.shape[2] * f.shape[3], dtype=torch.bool) for f in sc["src_views"]]
+        with torch.no_grad():
+            o = dec.layers[0](sc["tgt"], sc["query_pos"], sc["reference_points"][:, :, None], sc["src_views"],
+                              sc["spatial_shapes"], sc["level_start_index"], sc["meta"], masks, threshold=0.1)
+        out[f"{tag}_checksum"] = np.asarray([scene_checksum(sc, sd)])
+        for name, t in zip(("tgt", "ref", "refined2d", "proj2d", "prob"), o):
+            out[f"{tag}_{name}"] = t.numpy()
+    np.savez_compressed(os.path.join(GOLD, "decoder_configs.npz"), **out)
+
+
 def make_pose_sets(seed: int, n: int, dup_frac: float = 0.5):
     """Synthetic detections for the NMS fixture: clusters of near-duplicate T-poses (what
     neighbouring queries that converge on the same person look like) + isolated ones.
@@ -252,6 +282,7 @@ def main():
     gen_project_ref()
     gen_triangulate()
     gen_pre_post()
+    gen_decoder_other_configs()
     for fn in sorted(os.listdir(GOLD)):
         print(fn, os.path.getsize(os.path.join(GOLD, fn)))
 

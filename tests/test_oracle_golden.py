@@ -232,3 +232,28 @@ def test_assemble_predictions_semantics():
     _, kept = pp.postprocess(poses, prob, 0.3)
     for b in range(2):
         assert set(kept[b].tolist()) <= set(np.nonzero(pred[b, :, 0, 3].numpy() >= 0)[0].tolist())
+
+
+def test_decoder_layer_other_configs_vs_reference_golden():
+    """Oracle vs the reference's DQDecoderLayer.forward on the shapes of BASELINE configs[2..4]
+    (7 views, Shelf sizes, several frames per call): tests/golden/decoder_configs.npz."""
+    from oracle.gen_golden import OTHER_CONFIGS, other_config_scene
+    g = load_golden("decoder_configs.npz")
+    for tag, cfg_name, V, B, Q, levels in OTHER_CONFIGS:
+        sc, sd = other_config_scene(cfg_name, V, B, Q, levels)
+        assert scene_checksum(sc, sd) == str(g[f"{tag}_checksum"][0]), "synthetic generator drifted"
+        with torch.no_grad():
+            o = orc.decoder_layer_forward(orc.layer_params(sd, 0), sc["tgt"], sc["query_pos"],
+                                          sc["reference_points"], sc["src_views"], sc["spatial_shapes"],
+                                          sc["level_start_index"], sc["meta"], sc["img_size"], threshold=0.1)
+        gt = {k: torch.from_numpy(g[f"{tag}_{k}"]) for k in ("tgt", "ref", "refined2d", "proj2d", "prob")}
+        assert torch.allclose(o[0], gt["tgt"], atol=2e-5, rtol=1e-5), tag
+        assert torch.allclose(o[4], gt["prob"], atol=1e-6), tag
+        sel_g = gt["prob"][..., 1] > 0.1
+        assert torch.equal(o[4][..., 1] > 0.1, sel_g), tag                 # integer path
+        assert torch.equal(o[1] == 0, gt["ref"] == 0), tag                  # zero-fill pattern
+        assert torch.allclose(o[3], gt["proj2d"], atol=2e-4), tag
+        assert torch.allclose(o[2], gt["refined2d"], atol=3e-4), tag
+        if sel_g.any():
+            st = robust_3d_stats(o[1].view(B, Q, 15, 3), gt["ref"].view(B, Q, 15, 3), sel_g)
+            assert st["median"] < 0.1 and st["mean"] < 1.5, (tag, st)       # fp32-SVD noise floor
