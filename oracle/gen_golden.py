@@ -18,6 +18,7 @@ Fixtures (all produced by reference code, file:line given per entry):
                       (lib/mvn/utils/multiview.py:257-269), fp32 (as shipped) and the same
                       reference code fed float64 inputs (its exact-arithmetic answer)
   decoder_configs.npz one DQDecoderLayer.forward on the 7-view / Shelf / multi-frame shapes (BASELINE configs[2..4])
+  decoder_shelf_real.npz  the same with the cameras of the reference's data/Shelf/calibration_shelf.json
   pre_post.npz        sample_space reference points (lib/models/dq_transformer.py:298-323),
                       nearby_joints_nms keep lists (lib/core/nms.py:210-284), inverse_sigmoid
   state_dict_keys.json  parameter names/shapes of the reference DQDecoder
@@ -210,6 +211,47 @@ def gen_decoder_other_configs():
     np.savez_compressed(os.path.join(GOLD, "decoder_configs.npz"), **out)
 
 
+SHELF_REAL = dict(batch=2, num_instance=6, levels=((19, 25), (10, 13), (5, 7)), seed=41, weight_seed=19)
+
+
+def shelf_real_scene(cams):
+    """Scene on the REAL Shelf calibration (reference data file data/Shelf/calibration_shelf.json,
+    lib/dataset/shelf.py:233-242: 5 cameras, k = p = 0, 1032 x 776 images)."""
+    sc = syn.make_scene(syn.SHELF, batch=SHELF_REAL["batch"], n_views=len(cams),
+                        num_instance=SHELF_REAL["num_instance"], seed=SHELF_REAL["seed"],
+                        levels=SHELF_REAL["levels"], cams=cams)
+    sd = syn.make_decoder_state_dict(1, np.random.default_rng(SHELF_REAL["weight_seed"]), offset_px=1.0)
+    return sc, sd
+
+
+def gen_shelf_real():
+    """tests/golden/decoder_shelf_real.npz: one reference DQDecoderLayer.forward with the cameras of
+    the reference's own Shelf calibration file; the camera parameters are stored in the fixture so
+    that the tests rebuild the scene without the reference tree."""
+    path = os.path.join(os.environ.get("MVG_REFERENCE_ROOT", "/root/reference"), "data", "Shelf",
+                        "calibration_shelf.json")
+    raw = json.load(open(path))
+    cams = []
+    for cid in sorted(raw, key=int):
+        c = raw[cid]
+        cams.append(dict(R=np.array(c["R"], dtype=np.float64), T=np.array(c["T"], dtype=np.float64),
+                         fx=np.array(c["fx"], dtype=np.float64), fy=np.array(c["fy"], dtype=np.float64),
+                         cx=np.array(c["cx"], dtype=np.float64), cy=np.array(c["cy"], dtype=np.float64),
+                         k=np.array(c["k"], dtype=np.float64), p=np.array(c["p"], dtype=np.float64)))
+    sc, sd = shelf_real_scene(cams)
+    dec = build_reference_decoder(sc, sd, 1)
+    masks = [torch.zeros(f.shape[0], f.shape[2] * f.shape[3], dtype=torch.bool) for f in sc["src_views"]]
+    with torch.no_grad():
+        o = dec.layers[0](sc["tgt"], sc["query_pos"], sc["reference_points"][:, :, None], sc["src_views"],
+                          sc["spatial_shapes"], sc["level_start_index"], sc["meta"], masks, threshold=0.1)
+    out = {"checksum": np.asarray([scene_checksum(sc, sd)])}
+    for k in ("R", "T", "fx", "fy", "cx", "cy", "k", "p"):
+        out[f"cam_{k}"] = np.stack([c[k] for c in cams])
+    for name, t in zip(("tgt", "ref", "refined2d", "proj2d", "prob"), o):
+        out[name] = t.numpy()
+    np.savez_compressed(os.path.join(GOLD, "decoder_shelf_real.npz"), **out)
+
+
 def make_pose_sets(seed: int, n: int, dup_frac: float = 0.5):
     """Synthetic detections for the NMS fixture: clusters of near-duplicate T-poses (what
     neighbouring queries that converge on the same person look like) + isolated ones.
@@ -283,6 +325,7 @@ def main():
     gen_triangulate()
     gen_pre_post()
     gen_decoder_other_configs()
+    gen_shelf_real()
     for fn in sorted(os.listdir(GOLD)):
         print(fn, os.path.getsize(os.path.join(GOLD, fn)))
 

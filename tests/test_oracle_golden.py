@@ -257,3 +257,30 @@ def test_decoder_layer_other_configs_vs_reference_golden():
         if sel_g.any():
             st = robust_3d_stats(o[1].view(B, Q, 15, 3), gt["ref"].view(B, Q, 15, 3), sel_g)
             assert st["median"] < 0.1 and st["mean"] < 1.5, (tag, st)       # fp32-SVD noise floor
+
+
+def test_decoder_layer_real_shelf_calibration_vs_reference_golden():
+    """Oracle vs the reference layer run with the cameras of the reference's own Shelf calibration
+    file (stored in the fixture): tests/golden/decoder_shelf_real.npz."""
+    from oracle.gen_golden import shelf_real_scene
+    g = load_golden("decoder_shelf_real.npz")
+    cams = [{k: g[f"cam_{k}"][i] for k in ("R", "T", "fx", "fy", "cx", "cy", "k", "p")}
+            for i in range(g["cam_R"].shape[0])]
+    assert len(cams) == 5 and all(float(np.abs(c["k"]).max()) == 0.0 for c in cams)      # shelf: no distortion
+    sc, sd = shelf_real_scene(cams)
+    assert scene_checksum(sc, sd) == str(g["checksum"][0]), "synthetic generator drifted"
+    with torch.no_grad():
+        o = orc.decoder_layer_forward(orc.layer_params(sd, 0), sc["tgt"], sc["query_pos"], sc["reference_points"],
+                                      sc["src_views"], sc["spatial_shapes"], sc["level_start_index"], sc["meta"],
+                                      sc["img_size"], threshold=0.1)
+    gt = {k: torch.from_numpy(g[k]) for k in ("tgt", "ref", "refined2d", "proj2d", "prob")}
+    B, Q = gt["prob"].shape[:2]
+    assert torch.allclose(o[0], gt["tgt"], atol=2e-5, rtol=1e-5)
+    assert torch.allclose(o[4], gt["prob"], atol=1e-6)
+    sel_g = gt["prob"][..., 1] > 0.1
+    assert sel_g.any() and torch.equal(o[4][..., 1] > 0.1, sel_g)
+    assert torch.equal(o[1] == 0, gt["ref"] == 0)
+    assert torch.allclose(o[3], gt["proj2d"], atol=2e-4)
+    assert torch.allclose(o[2], gt["refined2d"], atol=3e-4)
+    st = robust_3d_stats(o[1].view(B, Q, 15, 3), gt["ref"].view(B, Q, 15, 3), sel_g)
+    assert st["median"] < 0.2 and st["mean"] < 2.0, st                                    # fp32-SVD noise floor
