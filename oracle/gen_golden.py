@@ -19,6 +19,7 @@ Fixtures (all produced by reference code, file:line given per entry):
                       reference code fed float64 inputs (its exact-arithmetic answer)
   decoder_configs.npz one DQDecoderLayer.forward on the 7-view / Shelf / multi-frame shapes (BASELINE configs[2..4])
   decoder_shelf_real.npz  the same with the cameras of the reference's data/Shelf/calibration_shelf.json
+  select_pad.npz      generate_valid_masks + padding_query_with_mask id arrays (dq_decoder.py:596-656)
   pre_post.npz        sample_space reference points (lib/models/dq_transformer.py:298-323),
                       nearby_joints_nms keep lists (lib/core/nms.py:210-284), inverse_sigmoid
   state_dict_keys.json  parameter names/shapes of the reference DQDecoder
@@ -252,6 +253,39 @@ def gen_shelf_real():
     np.savez_compressed(os.path.join(GOLD, "decoder_shelf_real.npz"), **out)
 
 
+SELECT_PAD_CASES = ((1, 7, 0.5, 51), (3, 100, 0.2, 52), (8, 1024, 0.5, 53), (2, 1500, 0.02, 54),
+                    (4, 64, 0.0, 55), (4, 64, 1.0, 56))          # (B, Q, selected fraction, seed)
+
+
+def select_pad_probs(B, Q, frac, seed):
+    """Class probabilities whose [..., 1] exceeds 0.5 for ~frac of the queries (ragged per frame)."""
+    rng = np.random.default_rng(seed)
+    p1 = np.where(rng.uniform(size=(B, Q)) < frac, rng.uniform(0.55, 1.0, size=(B, Q)),
+                  rng.uniform(0.0, 0.45, size=(B, Q)))
+    if B > 2 and 0.0 < frac < 1.0:
+        p1[1] = 0.1                                                 # one empty frame
+    prob = np.stack([rng.uniform(0.01, 1.0, size=(B, Q)), p1], -1).astype(np.float32)
+    return torch.from_numpy(prob)
+
+
+def gen_select_pad():
+    """tests/golden/select_pad.npz: DQDecoderLayer.generate_valid_masks + padding_query_with_mask
+    (lib/models/dq_decoder.py:596-656) - the integer path of the query filter - for ragged, empty and
+    full frames, methods 'threshold' and 'all'."""
+    sc, sd = small_scene()
+    layer = build_reference_decoder(sc, sd, SMALL["num_layers"]).layers[0]
+    out = {}
+    for B, Q, frac, seed in SELECT_PAD_CASES:
+        prob = select_pad_probs(B, Q, frac, seed)
+        for method in ("threshold", "all"):
+            b, q = layer.generate_valid_masks(prob, method=method, value=0.5)
+            bp, qp, br, qr = layer.padding_query_with_mask(b, q, B)
+            for name, t in zip(("b", "q", "bp", "qp", "br", "qr"), (b, q, bp, qp, br, qr)):
+                out[f"s{seed}_{method}_{name}"] = t.numpy().astype(np.int64)
+        out[f"s{seed}_sum"] = np.asarray([checksum(prob)])
+    np.savez_compressed(os.path.join(GOLD, "select_pad.npz"), **out)
+
+
 def make_pose_sets(seed: int, n: int, dup_frac: float = 0.5):
     """Synthetic detections for the NMS fixture: clusters of near-duplicate T-poses (what
     neighbouring queries that converge on the same person look like) + isolated ones.
@@ -326,6 +360,7 @@ def main():
     gen_pre_post()
     gen_decoder_other_configs()
     gen_shelf_real()
+    gen_select_pad()
     for fn in sorted(os.listdir(GOLD)):
         print(fn, os.path.getsize(os.path.join(GOLD, fn)))
 

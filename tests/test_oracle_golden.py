@@ -284,3 +284,20 @@ def test_decoder_layer_real_shelf_calibration_vs_reference_golden():
     assert torch.allclose(o[2], gt["refined2d"], atol=3e-4)
     st = robust_3d_stats(o[1].view(B, Q, 15, 3), gt["ref"].view(B, Q, 15, 3), sel_g)
     assert st["median"] < 0.2 and st["mean"] < 2.0, st                                    # fp32-SVD noise floor
+
+
+def test_select_pad_vs_reference_golden():
+    """Integer path of the query filter: oracle == the reference's generate_valid_masks +
+    padding_query_with_mask (dq_decoder.py:596-656) bit for bit, for ragged / empty / full frames
+    and both methods (tests/golden/select_pad.npz).  The GPU kernel is held to the same oracle
+    in tests/test_gpu_parity.py::test_select_pad_bit_exact."""
+    from oracle.gen_golden import SELECT_PAD_CASES, select_pad_probs, checksum as gsum
+    g = load_golden("select_pad.npz")
+    for B, Q, frac, seed in SELECT_PAD_CASES:
+        prob = select_pad_probs(B, Q, frac, seed)
+        assert gsum(prob) == str(g[f"s{seed}_sum"][0])
+        for method in ("threshold", "all"):
+            b, q = orc.generate_valid_masks(prob, method, 0.5)
+            bp, qp, br, qr = orc.padding_query_with_mask(b, q, B)
+            for name, t in zip(("b", "q", "bp", "qp", "br", "qr"), (b, q, bp, qp, br, qr)):
+                assert np.array_equal(t.numpy().astype(np.int64), g[f"s{seed}_{method}_{name}"]), (seed, method, name)
