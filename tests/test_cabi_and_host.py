@@ -137,3 +137,16 @@ def test_sample_params_struct_matches_header():
             names.append(re.sub(r"\[.*?\]", "", part.split()[-1]).strip())
     assert names == [n for n, _ in _lib.MvgSampleParams._fields_], (names, _lib.MvgSampleParams._fields_)
     assert ctypes.sizeof(_lib.MvgSampleParams) == 4 * 20 + 8
+
+
+def test_missing_library_fails_loudly():
+    """No CPU / eager fallback: with the shared library absent the first use raises MvgError
+    (checked in a fresh interpreter so that the loaded-library cache of this process is untouched)."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); os.environ['MVG_LIB_PATH'] = '/nonexistent/libmvg_b200.so'\n"
+            "from mvgformer_b200 import _lib\n"
+            "try:\n    _lib.load()\nexcept _lib.MvgError as e:\n    assert 'no CPU fallback' in str(e), str(e); print('raised')\n"
+            "else:\n    print('loaded')\n") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.stdout.strip().splitlines()[-1] == "raised", (out.stdout, out.stderr[-500:])
