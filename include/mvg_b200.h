@@ -40,6 +40,7 @@ extern "C" {
 #define MVG_MAX_LEVELS 4
 #define MVG_MAX_VIEWS 8
 #define MVG_CAM_FLOATS 64 /* floats per packed camera record, see MvgCamera in csrc/common.cuh */
+#define MVG_CAM_FIELDS 11 /* raw tensors per view consumed by mvg_pack_cameras */
 
 enum {
   MVG_OK = 0,
@@ -48,7 +49,7 @@ enum {
   MVG_EUNSUPPORTED = -3
 };
 
-enum { MVG_F32 = 0, MVG_BF16 = 1 };
+enum { MVG_F32 = 0, MVG_BF16 = 1, MVG_F64 = 2, MVG_F16 = 3 };
 
 /* Message for the last non-zero return on this thread. */
 MVG_API const char* mvg_last_error(void);
@@ -56,6 +57,21 @@ MVG_API const char* mvg_last_error(void);
 MVG_API int mvg_abi_version(void);
 /* Number of kernels launched by this library in this process (for bench accounting). */
 MVG_API int64_t mvg_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Camera packing: the raw `meta[v]` tensors of lib/dataset/JointsDataset.py:197-220 (batch-first
+ * after DataLoader collation) -> cams (B, V, MVG_CAM_FLOATS) fp32 records, ONE launch, no cache.
+ * Restates unfold_camera_param_batch (lib/utils/cameras.py:118-133), get_affine_transform(center,
+ * scale, 0, img_size) (lib/utils/transforms.py:72-112 - host numpy + cv2 per (view, frame, layer) in
+ * the reference, lib/models/dq_decoder.py:361-372), inv_affine_trans[:, :2] (:414-418),
+ * get_calib_matrix / K^-1 / P = K [R | -R T] (:207-246) and the clamp bound of :383.
+ *   fields: HOST array of views * MVG_CAM_FIELDS DEVICE pointers, per view in this order:
+ *     R (B,3,3), T (B,3,1), fx, fy, cx, cy (B), k (B,3,1), p (B,2,1), center (B,2), scale (B,2),
+ *     inv_affine_trans (B,3,3) - all contiguous; dtypes: matching HOST array of MVG_F32 / MVG_F64.
+ *   The pointer table is read at call time (captured by value in a CUDA graph).
+ */
+MVG_API int mvg_pack_cameras(const void* const* fields, const int* dtypes, int batch, int views,
+                     float img_w, float img_h, float* cams, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Deformable.deform_forward  (lib/models/ops/src/deform.h:31-50,

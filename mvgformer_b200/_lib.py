@@ -15,10 +15,11 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MVG_LIB_PATH", os.path.join(_HERE, "libmvg_b200.so"))   # override: A/B experiments
 
-MVG_F32, MVG_BF16 = 0, 1
+MVG_F32, MVG_BF16, MVG_F64, MVG_F16 = 0, 1, 2, 3
+MVG_CAM_FIELDS = 11
 MVG_MAX_LEVELS = 4
 MVG_CAM_FLOATS = 64
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class MvgError(RuntimeError):
@@ -58,6 +59,7 @@ SIGNATURES = {
     "mvg_ffn_chain": [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _F, _L, _I, _P, _P],
     "mvg_init_queries": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "mvg_assemble_predictions": [_P, _P, _I, _I, _I, _F, _P, _P, _P, _P],
+    "mvg_pack_cameras": [_P, _P, _I, _I, _F, _F, _P, _P],
     "mvg_nearby_joints_nms": [_P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P],
 }
 

@@ -1,12 +1,13 @@
-"""Camera packing: meta dicts -> one (B, V, 64) fp32 record array for the CUDA kernels.
+"""Camera packing: `meta` dicts -> one (B, V, 64) fp32 record array for the CUDA kernels.
 
-Host-side mirror (tiny tensor ops on the meta's own device, no host sync) of
+ONE launch of mvg_pack_cameras (csrc/cameras.cu) on the raw camera tensors, every call: no
+cache, nothing keyed on tensor addresses, graph-capturable.  In the reference loop `meta` is
+re-created by `.to(device)` every frame (lib/core/function.py:373-375), so this runs per frame.
+What the kernel restates:
   * unfold_camera_param_batch            lib/utils/cameras.py:118-133 (float32 casts)
   * get_affine_transform(center, scale, 0, img_size)   lib/utils/transforms.py:72-112, which
     the reference evaluates on the HOST with numpy + cv2 per (view, frame, layer)
-    (lib/models/dq_decoder.py:361-372).  For rot = 0 the three point pairs describe an
-    (almost) isotropic scale + shift; the same float32-rounded point pairs are solved here
-    exactly (float64 adjugate) on the device.
+    (lib/models/dq_decoder.py:361-372)
   * meta['inv_affine_trans'][:, :2, :]   lib/models/dq_decoder.py:414-418
   * get_calib_matrix / K.inverse() / get_proj_matricies_batch(inv_trans=True)
                                          lib/models/dq_decoder.py:207-246, :171
@@ -14,102 +15,51 @@ Record layout = struct MvgCamera in csrc/common.cuh.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Dict, List, Sequence
 
 import torch
 
-from ._lib import MVG_CAM_FLOATS
+from . import _lib
+from ._lib import MVG_CAM_FIELDS, MVG_CAM_FLOATS
 
-_cache: Dict[tuple, torch.Tensor] = {}
-
-
-def _solve_affine3(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
-    """Exact affine through 3 point pairs (what cv2.getAffineTransform solves).
-    src, dst (B,3,2) float64 -> (B,2,3).  Explicit adjugate, no library call / host sync."""
-    x0, y0 = src[:, 0, 0], src[:, 0, 1]
-    x1, y1 = src[:, 1, 0], src[:, 1, 1]
-    x2, y2 = src[:, 2, 0], src[:, 2, 1]
-    det = x0 * (y1 - y2) - y0 * (x1 - x2) + (x1 * y2 - x2 * y1)
-    # inverse of [[x0,y0,1],[x1,y1,1],[x2,y2,1]] = adj / det
-    inv = torch.stack([
-        torch.stack([y1 - y2, y2 - y0, y0 - y1], -1),
-        torch.stack([x2 - x1, x0 - x2, x1 - x0], -1),
-        torch.stack([x1 * y2 - x2 * y1, x2 * y0 - x0 * y2, x0 * y1 - x1 * y0], -1)], 1) / det[:, None, None]
-    return torch.matmul(inv, dst).transpose(1, 2).contiguous()      # (B,2,3)
+_FIELDS = ("R", "T", "fx", "fy", "cx", "cy", "k", "p")
+_NUMEL = dict(R=9, T=3, fx=1, fy=1, cx=1, cy=1, k=3, p=2, center=2, scale=2, inv_affine_trans=9)
 
 
-def _affine_rot0(center: torch.Tensor, scale: torch.Tensor, out_size: Sequence[float]) -> torch.Tensor:
-    """(B,2),(B,2) -> (B,2,3) float64; same point construction as transforms.py:84-110 (rot=0)."""
-    c = center.double()
-    st = scale.double() * 200.0
-    src_w, src_h = st[:, 0], st[:, 1]
-    dst_w, dst_h = float(out_size[0]), float(out_size[1])
-    wide = (src_w >= src_h).unsqueeze(1)
-    f32 = lambda t: t.float().double()       # the reference stores the points as float32
-    zero = torch.zeros_like(src_w)
-    src_dir = torch.where(wide, torch.stack([zero, src_w * -0.5], 1), torch.stack([src_h * -0.5, zero], 1))
-    dd_w = c.new_tensor([0.0, dst_w * -0.5]).float().double().expand_as(c)
-    dd_h = c.new_tensor([dst_h * -0.5, 0.0]).float().double().expand_as(c)
-    dst_dir = torch.where(wide, dd_w, dd_h)
-
-    def third(a, b):                          # get_3rd_point, float32 result
-        d = a - b
-        return f32(b + f32(torch.stack([-d[:, 1], d[:, 0]], 1)))
-
-    src0 = f32(c)
-    src1 = f32(c + src_dir)
-    dst0 = f32(c.new_tensor([dst_w * 0.5, dst_h * 0.5]).expand_as(c))
-    dst1 = f32(c.new_tensor([dst_w * 0.5, dst_h * 0.5]).expand_as(c) + dst_dir)
-    src = torch.stack([src0, src1, third(src0, src1)], 1)
-    dst = torch.stack([dst0, dst1, third(dst0, dst1)], 1)
-    return _solve_affine3(src, dst)
+def _field(t: torch.Tensor, name: str, batch: int, dev) -> torch.Tensor:
+    if t.device != dev:
+        t = t.to(dev)
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.double()
+    if t.numel() != batch * _NUMEL[name]:
+        raise _lib.MvgError(f"pack_cameras: {name} has {t.numel()} elements, expected {batch} x {_NUMEL[name]}")
+    return t if t.is_contiguous() else t.contiguous()
 
 
-def pack_cameras(meta: List[Dict], img_size: Sequence[float], device=None,
-                 use_cache: bool = True) -> torch.Tensor:
+def pack_cameras(meta: List[Dict], img_size: Sequence[float], device=None) -> torch.Tensor:
     """meta: list[V] of {'camera': {R,T,fx,fy,cx,cy,k,p}, 'center', 'scale',
     'inv_affine_trans'} batch-first tensors -> (B, V, MVG_CAM_FLOATS) float32 on `device`."""
-    key = None
-    if use_cache:
-        parts = [tuple(float(x) for x in img_size), str(device)]
-        for m in meta:
-            for t in list(m["camera"].values()) + [m["center"], m["scale"], m["inv_affine_trans"]]:
-                parts.append((t.data_ptr(), t._version, tuple(t.shape)))
-        key = tuple(parts)
-        hit = _cache.get(key)
-        if hit is not None:
-            return hit
-    recs = []
+    lib = _lib.load()
+    dev = torch.device(device) if device is not None else meta[0]["camera"]["R"].device
+    if dev.type != "cuda":
+        raise _lib.MvgError("Not implemented on the CPU")
+    V = len(meta)
+    B = int(meta[0]["camera"]["R"].shape[0])
+    keep, ptrs, dts = [], [], []
     for m in meta:
         cam = m["camera"]
-        dev = device if device is not None else cam["R"].device
-        f = lambda t: t.to(device=dev, dtype=torch.float32)
-        R = f(cam["R"])                                         # (B,3,3)
-        B = R.shape[0]
-        T = f(cam["T"]).reshape(B, 3, 1)
-        fx, fy, cx, cy = (f(cam[k]).reshape(B) for k in ("fx", "fy", "cx", "cy"))
-        kk = f(cam["k"]).reshape(B, 3)
-        pp = f(cam["p"]).reshape(B, 2)
-        center = m["center"].to(dev)
-        aff = _affine_rot0(center, m["scale"].to(dev), img_size).float()          # (B,2,3)
-        inv_aff = f(m["inv_affine_trans"])[:, :2, :]
-        K = torch.zeros(B, 3, 3, dtype=torch.float32, device=dev)
-        K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = fx, fy, cx, cy, 1.0
-        P = K.matmul(torch.cat([R, -R @ T], -1))                # (B,3,4)
-        Kinv = torch.zeros_like(K)
-        Kinv[:, 0, 0], Kinv[:, 1, 1], Kinv[:, 2, 2] = 1.0 / fx, 1.0 / fy, 1.0
-        Kinv[:, 0, 2], Kinv[:, 1, 2] = -cx / fx, -cy / fy
-        wh = (center.double() * 2).float()                      # (B,2)
-        clamp_max = wh.max().reshape(1, 1).expand(B, 1)         # dq_decoder.py:383 (whole tensor)
-        rec = torch.cat([R.reshape(B, 9), T.reshape(B, 3), fx[:, None], fy[:, None], cx[:, None],
-                         cy[:, None], kk, pp, aff.reshape(B, 6), inv_aff.reshape(B, 6),
-                         P.reshape(B, 12), Kinv.reshape(B, 9), wh, clamp_max,
-                         torch.zeros(B, 7, dtype=torch.float32, device=dev)], dim=1)
-        assert rec.shape[1] == MVG_CAM_FLOATS
-        recs.append(rec)
-    out = torch.stack(recs, dim=1).contiguous()                 # (B,V,64)
-    if key is not None:
-        if len(_cache) > 64:
-            _cache.clear()
-        _cache[key] = out
+        ts = [_field(cam[k], k, B, dev) for k in _FIELDS] + \
+             [_field(m[k], k, B, dev) for k in ("center", "scale", "inv_affine_trans")]
+        keep += ts
+        ptrs += [t.data_ptr() for t in ts]
+        dts += [_lib.MVG_F64 if t.dtype == torch.float64 else _lib.MVG_F32 for t in ts]
+    assert len(ptrs) == V * MVG_CAM_FIELDS
+    out = torch.empty((B, V, MVG_CAM_FLOATS), dtype=torch.float32, device=dev)
+    _lib.check(lib.mvg_pack_cameras((C.c_void_p * len(ptrs))(*ptrs), (C.c_int * len(dts))(*dts), B, V,
+                                    float(img_size[0]), float(img_size[1]), out.data_ptr(),
+                                    _lib.stream_ptr(dev)), "mvg_pack_cameras")
+    # converted copies (if any) must outlive the launch: torch's caching allocator keeps a block
+    # freed on this stream from being reused before the kernel that reads it, so dropping is safe
+    del keep
     return out

@@ -214,8 +214,12 @@ nms_greedy_kernel(const float* __restrict__ pred, const int* __restrict__ valid_
       const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
       if (ob > best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
     }
-    // a pose is always close to itself, so best_k is valid
-    if (!((ignored[best_k >> 5] >> (best_k & 31)) & 1u)) {
+    // a pose is always close to itself, so best_k is valid.  The ignored bit is read by ONE lane
+    // and broadcast, and the warp re-converges before any lane updates the bit set, so every lane
+    // takes the same branch (no read / write race on `ignored` under independent thread scheduling).
+    const uint32_t ign_word = __shfl_sync(0xffffffffu, ignored[best_k >> 5], 0);
+    __syncwarp();
+    if (!((ign_word >> (best_k & 31)) & 1u)) {
       if (lane == 0) {
         keep_compact[static_cast<int64_t>(b) * queries + cnt] = best_k;
         keep_query[static_cast<int64_t>(b) * queries + cnt] = vid[best_k];

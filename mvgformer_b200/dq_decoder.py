@@ -222,6 +222,12 @@ class DQDecoderLayer(nn.Module):
     # ------------------------------------------------------------------ the layer
     def _forward_ctx(self, tgt, query_pos, reference_points, ctx: DecoderContext, *,
                      threshold, indices=None, return_debug=False, shard=None):
+        if self.training or (torch.is_grad_enabled() and any(
+                t is not None and t.requires_grad for t in (tgt, query_pos, reference_points))):
+            # the fused path detaches its inputs and applies no dropout: refuse to pretend
+            raise NotImplementedError(
+                "mvgformer_b200.DQDecoderLayer is inference-only (call .eval() and run under "
+                "torch.no_grad()); training goes through the op-level DeformFunction drop-in")
         B, N, C = tgt.shape
         J = self.num_joints
         Q = N // J
@@ -239,8 +245,8 @@ class DQDecoderLayer(nn.Module):
         value_hm, gmap = ctx.vg_for(self)
         prm = ops.make_sample_params(B, V, N, ctx.levels, ctx.ld_g, ctx.img_size, ctx.value_head_stride)
         with prof.stage("project_sample_fused"):
-            sampled, ref2d, bounding = ops.project_sample_fused(ref3d, ctx.cams, value_hm, gmap, qproj, prm)
-        prof.note("inview_items", ops._last_work[:B * V].sum())   # no-op unless profiling is enabled
+            sampled, ref2d, bounding, work = ops.project_sample_fused(ref3d, ctx.cams, value_hm, gmap, qproj, prm)
+        prof.note("inview_items", lambda: work[:B * V].sum())     # evaluated only when profiling is enabled
         # 4. output_proj, mask, view-mean, update MLP, LN, FFN, LN
         with prof.stage("output_proj"):
             # (B,V,N,256) bf16, rows of out-of-view points zeroed in the epilogue (:585-586)
@@ -266,7 +272,12 @@ class DQDecoderLayer(nn.Module):
             for b, qs in enumerate(indices):
                 if len(qs):
                     selected[b, torch.as_tensor(qs, device=tgt.device, dtype=torch.long)] = 1
-            selected[0, 0] |= (selected.sum() == 0).to(torch.uint8)              # :620-623
+            if shard is None:
+                selected[0, 0] |= (selected.sum() == 0).to(torch.uint8)          # :620-623
+            else:
+                self._shard_count = selected.sum().to(torch.int32).reshape(1)
+                if len(shard) > 3 and shard[3] and shard[0] == 0:
+                    selected[0, 0] = 1
         else:
             method = "threshold" if self.filter_query else "all"
             selected, _, info = ops.select_pad(prob, threshold, method, min_one=shard is None)

@@ -70,9 +70,6 @@ def linear_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
     return out
 
 
-_last_work: Optional[torch.Tensor] = None
-
-
 def value_proj(feat_cl: torch.Tensor, w_all: torch.Tensor, b_all: Optional[torch.Tensor], layers: int):
     """The pyramid projections of `layers` decoder layers in one GEMM, in the gather's layouts.
     feat_cl (rows, S, 256) bf16; w_all (layers*448, 256) bf16 = per layer [rayconv | sampling_offsets |
@@ -97,9 +94,6 @@ def value_proj(feat_cl: torch.Tensor, w_all: torch.Tensor, b_all: Optional[torch
     return value_hm, gmap
 
 
-_last_work: Optional[torch.Tensor] = None
-
-
 def make_sample_params(batch: int, views: int, points: int, levels: Sequence[Tuple[int, int]],
                        ld_g: int, img_size: Sequence[float], value_head_stride: int) -> MvgSampleParams:
     prm = MvgSampleParams()
@@ -121,7 +115,8 @@ def project_sample_fused(ref3d: Optional[torch.Tensor], cams: Optional[torch.Ten
                          prm: MvgSampleParams, refl: Optional[torch.Tensor] = None):
     """value_hm: this layer's 8 heads of the head-major value tensor (8, rows*S, 32); gmap: this
     layer's 192 columns of G (a column slice, row stride prm.ld_g).
-    -> sampled (B,V,N,256) bf16, ref2d (B,V,N,2) fp32, bounding (B,V,N) uint8."""
+    -> sampled (B,V,N,256) bf16, ref2d (B,V,N,2) fp32, bounding (B,V,N) uint8, work (the int32
+    workspace, [:B*V] = in-view item counts per (frame, view); None on the ProjAttn entry)."""
     lib = _lib.load()
     dev = value_hm.device
     B, V, N = prm.batch, prm.views, prm.points
@@ -134,9 +129,7 @@ def project_sample_fused(ref3d: Optional[torch.Tensor], cams: Optional[torch.Ten
                                        qproj.data_ptr(), C.byref(prm), sampled.data_ptr(),
                                        ref2d.data_ptr(), bounding.data_ptr(), _lib.ptr(refl),
                                        _lib.ptr(work), stream_ptr(dev)), "mvg_project_sample_fused")
-    global _last_work
-    _last_work = work          # diagnostics only (profiling.note in dq_decoder): [:B*V] = in-view counts
-    return sampled, ref2d, bounding
+    return sampled, ref2d, bounding, work
 
 
 def select_pad(prob: torch.Tensor, threshold: float, method: str = "threshold",

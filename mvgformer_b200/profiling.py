@@ -37,10 +37,13 @@ def counters() -> Dict[str, int]:
     return dict(_counters)
 
 
-def note(name: str, value: torch.Tensor) -> None:
+def note(name: str, value) -> None:
     """Keeps a (cloned) device scalar for later inspection, e.g. the number of in-view items the
-    gather processed; no synchronisation happens here."""
+    gather processed; no synchronisation happens here.  `value` may be a zero-argument callable:
+    it is only evaluated when profiling is enabled, so a disabled note enqueues nothing."""
     if _enabled:
+        if callable(value) and not isinstance(value, torch.Tensor):
+            value = value()
         _notes[name].append(value.detach().clone() if callable(getattr(value, "detach", None)) else value)
 
 

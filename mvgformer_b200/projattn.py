@@ -138,6 +138,6 @@ class ProjAttn(nn.Module):
         qproj = linear(query.to(torch.bfloat16), w["w_q"], w["b_q"], out_dtype=torch.float32)
         prm = ops.make_sample_params(n_views, 1, Lq, levels, gmap.shape[-1], (1.0, 1.0), value_hm.stride(0))
         refl = reference_points.float().contiguous()
-        sampled, _, _ = ops.project_sample_fused(None, None, value_hm, gmap, qproj, prm, refl=refl)
+        sampled, _, _, _ = ops.project_sample_fused(None, None, value_hm, gmap, qproj, prm, refl=refl)
         out = linear(sampled.view(n_views, Lq, 256), w["w_o"], w["b_o"], out_dtype=torch.float32)
         return out

@@ -58,11 +58,14 @@ class QueryInit(nn.Module):
         qpos = torch.empty((batch, Q * J, C), dtype=torch.float32, device=dev)
         ref = torch.empty((batch, Q * J, 3), dtype=torch.float32, device=dev)
         import ctypes as Cc
+        # module.float() / .half() / .to(dtype) also cast the buffers: hand the kernel the dtypes it reads
+        lin = self._lin.detach().to(device=dev, dtype=torch.float32).contiguous()
+        tpose = self.t_pose_origin.detach().to(device=dev, dtype=torch.float64).contiguous()
         size = (Cc.c_float * 3)(*self.grid_size)
         cen = (Cc.c_float * 3)(*self.grid_center)
         check(lib.mvg_init_queries(w.detach().float().contiguous().data_ptr(),
                                    self.instance_embedding.weight.detach().float().contiguous().data_ptr(),
-                                   self._lin.data_ptr(), self.t_pose_origin.data_ptr(), size, cen,
+                                   lin.data_ptr(), tpose.data_ptr(), size, cen,
                                    batch, Q, J, C, int(self._lin.numel()), qpos.data_ptr(), tgt.data_ptr(),
                                    ref.data_ptr(), stream_ptr(dev)), "mvg_init_queries")
         return tgt, qpos, ref

@@ -394,7 +394,7 @@ def decoder_layer_forward(prm, tgt, query_pos, reference_points, src_views, spat
         dbg.update(batch_ids=b_pad, query_ids=q_pad, batch_ids_rev=b_rev, query_ids_rev=q_rev,
                    bounding=torch.stack(bounding_views, 1), ref2d=torch.stack(ref2d_views, 1),
                    attn_views=torch.stack(attn_views, 1), conf=conf_f, kp_undist=kp_und,
-                   proj_matrices=P, refined_valid=new_refined)
+                   proj_matrices=P, refined_valid=new_refined, b_valid=b_valid, q_valid=q_valid)
         return res, dbg
     return res
 

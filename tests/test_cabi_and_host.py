@@ -64,10 +64,15 @@ def test_unsupported_branches_raise():
 
 
 def test_camera_pack_matches_oracle_pieces():
+    """The torch mirror of the camera record (tests/camera_ref.py - the checker the GPU test holds
+    mvg_pack_cameras to) against the oracle's own pieces; the product packer itself has no CPU path."""
     from oracle import decoder_oracle as orc
+    from camera_ref import pack_cameras_torch
     for cfg in (syn.PANOPTIC, syn.SHELF):
         sc = syn.make_scene(cfg, batch=2, n_views=4, num_instance=4, seed=3, levels=((4, 4),) * 3)
-        pk = cameras.pack_cameras(sc["meta"], sc["img_size"], use_cache=False)
+        with pytest.raises(_lib.MvgError, match="Not implemented on the CPU"):
+            cameras.pack_cameras(sc["meta"], sc["img_size"])
+        pk = pack_cameras_torch(sc["meta"], sc["img_size"])
         assert pk.shape == (2, 4, _lib.MVG_CAM_FLOATS) and pk.dtype == torch.float32
         P = orc.proj_matrices([m["camera"] for m in sc["meta"]])             # (B,V,3,4)
         assert torch.allclose(pk[:, :, 33:45].reshape(2, 4, 3, 4), P, rtol=1e-6, atol=1e-3)

@@ -697,3 +697,72 @@ def test_decoder_tcgen05_matches_cublas_backend():
     hs_t, refs_t, _, _, cls_t = outs["tcgen05"]
     assert (hs_c[0] - hs_t[0]).abs().max() < 3e-2
     assert (cls_c[0] - cls_t[0]).abs().max() < 3e-3
+
+
+# ----------------------------------------------------------------------------- cameras (mvg_pack_cameras)
+@pytest.mark.parametrize("cfg_name,B,V,f32", [("PANOPTIC", 3, 5, False), ("SHELF", 2, 4, False),
+                                              ("PANOPTIC", 40, 7, True)])
+def test_pack_cameras_kernel_vs_torch_mirror(cfg_name, B, V, f32):
+    """mvg_pack_cameras (one launch on the raw meta tensors) against the torch mirror
+    tests/camera_ref.py, which the CPU suite pins to the oracle's pieces."""
+    from camera_ref import pack_cameras_torch
+    cfg = getattr(syn, cfg_name)
+    sc = syn.make_scene(cfg, batch=B, n_views=V, num_instance=2, seed=13, levels=((4, 4),) * 3)
+    if B > 2:       # frames with different crops / image sizes: the clamp bound is a per-view max
+        for m in sc["meta"]:
+            m["center"][1] *= 1.25
+            m["scale"][1] *= 1.25
+    meta = scene_to(sc, DEV)["meta"]
+    if f32:
+        meta = [{"camera": {k: v.float() for k, v in m["camera"].items()}, "center": m["center"].float(),
+                 "scale": m["scale"], "inv_affine_trans": m["inv_affine_trans"].float()} for m in meta]
+    got = cameras.pack_cameras(meta, sc["img_size"]).cpu()
+    ref = pack_cameras_torch([{"camera": {k: v.cpu() for k, v in m["camera"].items()}, "center": m["center"].cpu(),
+                               "scale": m["scale"].cpu(), "inv_affine_trans": m["inv_affine_trans"].cpu()}
+                              for m in meta], sc["img_size"])
+    assert got.shape == ref.shape == (B, V, 64)
+    exact = list(range(0, 21)) + list(range(27, 33)) + [54, 55, 56]    # R T f c k p | inv_aff | wh clamp_max
+    assert torch.equal(got[..., exact], ref[..., exact])
+    assert torch.allclose(got[..., 21:27], ref[..., 21:27], rtol=1e-6, atol=1e-6)      # affine
+    assert torch.allclose(got[..., 33:45], ref[..., 33:45], rtol=2e-7, atol=1e-6)      # P: <= 1 ulp (sum order)
+    assert torch.allclose(got[..., 45:54], ref[..., 45:54], rtol=2e-7, atol=0)         # K^-1
+    assert float(got[..., 57:].abs().max()) == 0.0
+
+
+def test_cameras_are_not_cached_by_address():
+    """`meta` is re-created every frame in the reference loop (lib/core/function.py:373-375); new
+    tensors land on recycled addresses with _version 0.  The packer must read their VALUES."""
+    sc = syn.make_scene(batch=1, n_views=3, num_instance=8, seed=3, levels=((20, 36), (10, 18), (5, 9)))
+    sd = syn.make_decoder_state_dict(1, np.random.default_rng(2), offset_px=1.0)
+    dec = make_decoder(sc, sd, 1)
+    scd = scene_to(sc, DEV)
+
+    def run(meta):
+        with torch.no_grad():
+            return dec(scd["tgt"], scd["reference_points"], scd["src_views"], meta, scd["spatial_shapes"],
+                       scd["level_start_index"], None, query_pos=scd["query_pos"], threshold=0.0)[1].clone()
+
+    def shifted(meta_cpu):       # a different calibration: cameras moved by 300 mm, longer focal length
+        out = []
+        for m in meta_cpu:
+            cam = {k: v.clone() for k, v in m["camera"].items()}
+            cam["T"] = cam["T"] + 300.0
+            cam["fx"] = cam["fx"] * 1.1
+            out.append({"camera": cam, "center": m["center"].clone(), "scale": m["scale"].clone(),
+                        "inv_affine_trans": m["inv_affine_trans"].clone()})
+        return out
+
+    to_dev = lambda ms: [{"camera": {k: v.to(DEV) for k, v in m["camera"].items()}, "center": m["center"].to(DEV),
+                          "scale": m["scale"].to(DEV), "inv_affine_trans": m["inv_affine_trans"].to(DEV)} for m in ms]
+    meta_b_ref = to_dev(shifted(sc["meta"]))           # allocated while meta A is still alive
+    want_b = run(meta_b_ref)
+    meta_a = to_dev(sc["meta"])
+    ptr_a = meta_a[0]["camera"]["T"].data_ptr()
+    out_a = run(meta_a)
+    del meta_a
+    meta_b = to_dev(shifted(sc["meta"]))               # same shapes, freed blocks are reused
+    recycled = meta_b[0]["camera"]["T"].data_ptr() == ptr_a
+    out_b = run(meta_b)
+    assert torch.equal(out_b, want_b)
+    assert not torch.equal(out_b, out_a)
+    assert recycled or True      # (informational: the allocator normally hands the same block back)
