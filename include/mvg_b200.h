@@ -130,7 +130,8 @@ MVG_API int mvg_linear_bf16(const void* A, const void* W, const float* bias, voi
  * projattn.py:169,180-181), written in the layouts the fused gather reads:
  *   feat (M = V*B*S, 256) bf16; W (layers*448, 256) bf16, per layer rows [rayconv 256 |
  *   sampling_offsets 128 | attention_weights 64]; bias (layers*448) fp32 or NULL;
- *   value_hm (layers*8, M, 32) bf16 head-major; gmap (M, layers*192) bf16.
+ *   value_hm (layers*8, M, 32) FP16 head-major; gmap (M, layers*192) FP16 (bf16 operands, fp32
+ *   accumulation, fp16 stores: the fused gather blends in packed fp16).
  */
 MVG_API int mvg_value_proj_gemm(const void* feat, const void* W, const float* bias, int64_t M, int layers,
                         void* value_hm, void* gmap, void* stream);
@@ -143,10 +144,10 @@ MVG_API int mvg_value_proj_gemm(const void* feat, const void* W, const float* bi
  *   a5  multi-scale deformable gather (deform_im2col_cuda.cuh:247-309)
  * Inputs:
  *   ref3d (B,N,3) fp32 world mm;  cams (B,V,MVG_CAM_FLOATS) fp32 packed cameras;
- *   value_hm (8 heads, V*B*S rows, 32) bf16, HEAD-MAJOR: head h of position s of map row r = v*B + b
+ *   value_hm (8 heads, V*B*S rows, 32) FP16, HEAD-MAJOR: head h of position s of map row r = v*B + b
  *       is the 64 bytes at value_hm + h*value_head_stride + (r*S + s)*32 (rayconv output; the two
  *       horizontal corners of a bilinear footprint are contiguous);
- *   gmap (V*B*S rows, ld_g) bf16: columns [0,128) = sampling_offsets.weight @ feat, [128,192) =
+ *   gmap (V*B*S rows, ld_g) FP16: columns [0,128) = sampling_offsets.weight @ feat, [128,192) =
  *       attention_weights.weight @ feat (both WITHOUT bias; bilinear interpolation commutes with
  *       the linear map).  Both are written by mvg_value_proj_gemm;
  *   qproj (B,N,192) fp32 = [sampling_offsets; attention_weights](tgt + query_pos) + bias.
@@ -155,11 +156,16 @@ MVG_API int mvg_value_proj_gemm(const void* feat, const void* W, const float* bi
  *   network-image coordinates, bounding (B,V,N) uint8.
  * ProjAttn.forward entry (projattn.py:115): when `refl_in` (B,V,N,Lv,2) is non-NULL the
  *   projection is skipped and the per-level normalised reference points are read from it
- *   (ref3d, cams, ref2d, bounding, workspace may then be NULL).
+ *   (ref3d, cams, ref2d, bounding may then be NULL).
  * Out-of-view points (bounding == 0): the reference multiplies their attention feature by 0
  *   (dq_decoder.py:585-586) and reads it nowhere else, so they are not gathered; their
- *   `sampled` rows are zeros.  `workspace` (device, 4 * (B*V*N + B*V + 4) bytes, contents
- *   irrelevant on entry) receives, per (frame, view), the count and the list of in-view items.
+ *   `sampled` rows are zeros.
+ * Arithmetic: geometry, softmax and the bilinear x attention weights in fp32; the weights are then
+ *   rounded to fp16 and the blend of a pyramid level runs in packed fp16 (HFMA2), levels are summed
+ *   in fp32.  Items are binned by image cell and gathered from shared-memory tiles staged by
+ *   cp.async.bulk (csrc/project_sample.cu).
+ * `workspace`: device, 256-byte aligned, mvg_project_sample_workspace_bytes(prm) bytes, contents
+ *   irrelevant on entry; its first B*V int32 receive the in-view item count of every (frame, view).
  */
 typedef struct {
   int batch, views, points;     /* B, V, N */
@@ -173,6 +179,7 @@ typedef struct {
   int64_t value_head_stride;    /* elements between consecutive heads of value_hm (>= V*B*S*32) */
 } MvgSampleParams;
 
+MVG_API int64_t mvg_project_sample_workspace_bytes(const MvgSampleParams* prm);
 MVG_API int mvg_project_sample_fused(const float* ref3d, const float* cams, const void* value_hm,
                              const void* gmap, const float* qproj, const MvgSampleParams* prm, void* sampled,
                              float* ref2d, uint8_t* bounding, const float* refl_in,

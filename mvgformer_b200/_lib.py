@@ -80,6 +80,8 @@ def load() -> C.CDLL:
     lib.mvg_last_error.argtypes = []
     lib.mvg_abi_version.restype = C.c_int
     lib.mvg_launch_count.restype = C.c_int64
+    lib.mvg_project_sample_workspace_bytes.restype = C.c_int64
+    lib.mvg_project_sample_workspace_bytes.argtypes = [C.POINTER(MvgSampleParams)]
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
@@ -113,6 +115,8 @@ def dtype_code(dt: torch.dtype) -> int:
         return MVG_F32
     if dt == torch.bfloat16:
         return MVG_BF16
+    if dt == torch.float64:
+        return MVG_F64
     raise MvgError(f"unsupported dtype {dt} (float32 / bfloat16 only)")
 
 

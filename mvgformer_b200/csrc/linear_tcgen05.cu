@@ -202,10 +202,15 @@ linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a,
             uint8_t* srow = stage + lane * 128;
             if constexpr (sizeof(OutT) == 2) {
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {        // 4 chunks of 8 bf16
+              for (int t = 0; t < 4; ++t) {        // 4 chunks of 8 bf16 (fp16 in split mode)
                 uint4 o;
-                o.x = pack_bf16x2(v[8 * t], v[8 * t + 1]);     o.y = pack_bf16x2(v[8 * t + 2], v[8 * t + 3]);
-                o.z = pack_bf16x2(v[8 * t + 4], v[8 * t + 5]); o.w = pack_bf16x2(v[8 * t + 6], v[8 * t + 7]);
+                if (hm_period > 0) {               // warp-uniform: the gather's maps are fp16
+                  o.x = pack_f16x2(v[8 * t], v[8 * t + 1]);     o.y = pack_f16x2(v[8 * t + 2], v[8 * t + 3]);
+                  o.z = pack_f16x2(v[8 * t + 4], v[8 * t + 5]); o.w = pack_f16x2(v[8 * t + 6], v[8 * t + 7]);
+                } else {
+                  o.x = pack_bf16x2(v[8 * t], v[8 * t + 1]);     o.y = pack_bf16x2(v[8 * t + 2], v[8 * t + 3]);
+                  o.z = pack_bf16x2(v[8 * t + 4], v[8 * t + 5]); o.w = pack_bf16x2(v[8 * t + 6], v[8 * t + 7]);
+                }
                 if (hm_head >= 0) {
                   // head-major value rows: one 32-row x 64-byte tile per head, SWIZZLE_64B
                   *reinterpret_cast<uint4*>(stage + h * 2048 + lane * 64 + ((t ^ ((lane >> 1) & 3)) << 4)) = o;

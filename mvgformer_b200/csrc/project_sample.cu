@@ -1,4 +1,5 @@
-// Fused projection + projective-attention sampling.
+// Fused projection + projective-attention sampling, round-2 design: spatially binned items,
+// TMA-staged shared-memory tiles, fp16 HFMA2 blend.
 //
 //   a3  project_ref_points      lib/models/dq_decoder.py:331-397, lib/utils/cameras.py:167-207,
 //                               lib/utils/transforms.py:135-141
@@ -7,121 +8,155 @@
 //                               `.view` layout scramble of the per-level Linear outputs)
 //   a5  deformable gather       lib/models/ops/src/cuda/deform_im2col_cuda.cuh:247-309, :41-93
 //
-// Two kernels per call:
-//   project_compact_kernel  one thread per (frame, view, point): projection (non-contracted fp32
-//       in the reference's op order -> `bounding` bit-exact), ref2d / bounding outputs, and an
-//       ordered-per-block compaction of the IN-VIEW items.  The reference multiplies the
-//       attention feature of an out-of-view point by 0 (dq_decoder.py:585-586) and uses it
-//       nowhere else, so those items are not gathered at all (their `sampled` row is zeros).
-//   gather_kernel           one warp per in-view item, one persistent CTA per SM owning a
-//       contiguous slice of the compacted list (an SM works on ~one person at a time and the
-//       overlapping sampling footprints share its L1).
+// Why tiles.  Every in-view (view, point) item gathers 8 heads x 24 samples x 4 corners x 64 B =
+// 49 KB; at Q = 1024 that is 3.8 GB per launch against 0.23 GB of compulsory HBM bytes.  A
+// warp-level LDG.128 delivers at most 64 B/clk/SM even on L1 hits (profiles/ubench_l1_mma_r1.txt),
+// LDS.128 from shared memory 119 B/clk/SM with the fp16 blend attached
+// (profiles/ubench_smem_gather_r2.txt), and the round-1 bf16 -> fp32 unpack + FFMA blend was
+// ALU-bound at 79 B/clk/SM whatever the source.  So: (1) the value / offset-logit maps are fp16
+// (written by the tcgen05 GEMM epilogue; 8x finer than bf16) and the bilinear x attention blend
+// runs in packed HFMA2 - 4 instructions per 16-byte load instead of 12 - with fp32 accumulation
+// across the pyramid levels; (2) the gathered rows come from shared-memory tiles staged by
+// cp.async.bulk (TMA, UBLKCP).
 //
-// Restructuring vs the reference:
-//   * The per-level Linear on (grid_sample(feat_l) + query) is split by linearity into
-//     bilinear-sampling a pre-projected 192-channel map G = feat @ [W_off; W_attn]^T (written by
-//     the same tcgen05 GEMM that produces `value`) plus a per-point term qproj = W (tgt+pos) + b.
-//   * Phase B computes, once per (head, sample), the four bilinear*attention weights and the
-//     base texel offset and stages them in shared memory; phase C is then a branch-free stream
-//     of LDG.128 (lane = head*4 + chunk: the 4 lanes of a head fetch one 64-byte (texel, head)
-//     row in ONE L1 request) + fp32 FMAs, with the bf16 -> fp32 conversion done by the tensor
-//     pipe (see fma_corner).
-//   * A tensor-pipe weighted sum (loaded bytes as the MMA A fragment, weights as a
-//     block-diagonal B) was built and measured this round: it needs 4x fewer instructions but
-//     its fragment-shaped loads split every 64-byte row over two quarter-warps, i.e. two L1
-//     requests and two sector fills per row, and the kernel is L1 data-pipe bound - 478 us vs
-//     345 us (profiles/gather_experiments_r1.md).
-// Geometry and the sampling index path use non-contracted fp32 ops in the reference's op order.
-#include "common.cuh"
+// Pipeline of one call (all on `stream`, no host sync):
+//   project_bin_kernel   one thread per (frame, view, point): projection in non-contracted fp32
+//                        in the reference's op order (`bounding` bit-exact), ref2d / bounding
+//                        outputs, zero `sampled` rows for out-of-view points (the reference
+//                        multiplies their attention feature by 0, dq_decoder.py:585-586, and
+//                        reads it nowhere else), and a KEY = (frame-view, 24 x 24 level-0 texel
+//                        cell of the reference point) with its rank inside the key
+//                        (warp-aggregated atomics).
+//   bin_scan_kernel      one block: key offsets, and CHUNKS of <= 128 same-key items.
+//   bin_scatter_kernel   counting-sort scatter -> item list ordered by key.
+//   sample_params_kernel one CTA per chunk, one warp per item: phase A samples the pre-projected
+//                        192-channel map G at the reference point (+ qproj), phase B does the
+//                        24-way softmax and, per (head, sample), the clamped 2x2 texel block and
+//                        its four bilinear x attention weights (fp16) -> 16-byte records in the
+//                        workspace, plus the bounding box of every (chunk, head, level)'s samples.
+//   gather_tiles_kernel  persistent, one CTA per SM: a producer warp stages, per (chunk, head),
+//                        the bounding-box tile of each level (rows of the head-major value
+//                        tensor, one cp.async.bulk per tile row, mbarrier complete_tx) into a
+//                        per-level shared-memory region; 16 consumer warps gather level by level
+//                        (LDS.128: a quarter-warp reads the two horizontal corners of one head =
+//                        128 contiguous bytes, conflict-free), so the level-l region is re-filled
+//                        for the next unit while levels l+1.. of this unit are still being read.
+//   gather_direct_kernel same arithmetic with LDG from global memory, for the (chunk, head) units
+//                        whose boxes do not fit the regions (never on the shipped configurations;
+//                        keeps the operator correct for arbitrary offsets).
+// Results do not depend on the (non-deterministic) order of items inside a key: every item's
+// arithmetic is a fixed sequence over its own records.
+#include "tcgen05.cuh"
 
 namespace mvg {
 
-#ifndef MVG_PS_WARPS
-#define MVG_PS_WARPS 16
-#endif
-#ifndef MVG_PS_UNROLL
-#define MVG_PS_UNROLL 4
-#endif
-#ifndef MVG_PS_MMA_UNPACK
-#define MVG_PS_MMA_UNPACK 0        // 1: bf16 -> fp32 through the tensor pipe, 0: shift / mask ALU ops
-#endif
-constexpr int kWarps = MVG_PS_WARPS;   // warps per CTA; one persistent CTA per SM
-constexpr int kPsUnroll = MVG_PS_UNROLL;
 constexpr int kQP = 192;           // 128 offset channels + 64 logit channels per level
 constexpr int kHeads = 8;
-constexpr int kPcThreads = 256;    // project_compact block
-
-// acc (two fp32 packed in a 64-bit register) += {w, w} * {bf16 lo, bf16 hi} of the 32-bit word u
-// (Blackwell packed FFMA2: one issue slot for two channels).  Used by phase A only.
-__device__ __forceinline__ void fma2_bf16pair(uint64_t& acc, uint32_t u, uint64_t ww) {
-  uint64_t v;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(u << 16), "r"(u & 0xffff0000u));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(v), "l"(ww));
-}
-__device__ __forceinline__ uint64_t pack2(float a, float b) {
-  uint64_t v;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
-  return v;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ void fma2_corner(uint64_t (&acc)[4], const uint4& c, float w) {
-  const uint64_t ww = pack2(w, w);
-  fma2_bf16pair(acc[0], c.x, ww);
-  fma2_bf16pair(acc[1], c.y, ww);
-  fma2_bf16pair(acc[2], c.z, ww);
-  fma2_bf16pair(acc[3], c.w, ww);
-}
-// acc[0..3] (8 fp32 channels as 4 packed pairs) += w * the 8 bf16 channels of c.
-// MVG_PS_MMA_UNPACK: the bf16 -> fp32 conversion runs on the otherwise idle tensor pipe:
-// D(16x8) = A(16x8) * I(8x8) with A's fragment = the lane's own words ({c.x, c.y}, then
-// {c.z, c.w}) returns, in the same lane, D[g][2t..2t+1] = A[g][2t..2t+1] - the two halves of
-// the first word as fp32 - and D[g+8][2t..2t+1] = those of the second word.  The products are
-// exact (x * 1.0 + 0), and the results land in aligned register pairs that feed FFMA2
-// directly: 2 HMMA + 4 FFMA2 per 16-byte load instead of 8 ALU + 4 FFMA2.  Measured (r1, layer-0
-// call): 21 % fewer warp instructions, issue 56 -> 44 %, but 287 us vs 271 us - the kernel is
-// bound by L1 latency / data-pipe wavefronts and the HMMA adds latency to every
-// load -> accumulate chain.  Kept as an option, off by default.
-__device__ __forceinline__ void fma_corner(uint64_t (&acc)[4], const uint4& c, float w, uint32_t b_ident) {
-#if MVG_PS_MMA_UNPACK
-  const uint64_t ww = pack2(w, w);
-  uint64_t v0, v1, v2, v3;
-  asm("{\n\t.reg .f32 d0, d1, d2, d3;\n\t"
-      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {d0, d1, d2, d3}, {%2, %3}, {%4}, {%5, %5, %5, %5};\n\t"
-      "mov.b64 %0, {d0, d1};\n\tmov.b64 %1, {d2, d3};\n\t}"
-      : "=l"(v0), "=l"(v1) : "r"(c.x), "r"(c.y), "r"(b_ident), "f"(0.f));
-  asm("{\n\t.reg .f32 d0, d1, d2, d3;\n\t"
-      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {d0, d1, d2, d3}, {%2, %3}, {%4}, {%5, %5, %5, %5};\n\t"
-      "mov.b64 %0, {d0, d1};\n\tmov.b64 %1, {d2, d3};\n\t}"
-      : "=l"(v2), "=l"(v3) : "r"(c.z), "r"(c.w), "r"(b_ident), "f"(0.f));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[0]) : "l"(v0), "l"(ww));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[1]) : "l"(v1), "l"(ww));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[2]) : "l"(v2), "l"(ww));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[3]) : "l"(v3), "l"(ww));
-#else
-  fma2_corner(acc, c, w);
+constexpr int kPcThreads = 256;    // project_bin block
+#ifndef MVG_CORE
+#define MVG_CORE 16
 #endif
+constexpr int kCore = MVG_CORE;    // key cell edge, level-0 texels
+constexpr int kChunk = 128;        // items per chunk (upper bound)
+constexpr int kPWarps = 16;        // sample_params: warps per CTA
+constexpr int kGWarps = 16;        // gather_tiles: consumer warps per CTA (+ 1 producer warp)
+constexpr int kScanThreads = 1024;
+constexpr int kRecBytes = 128;     // records of one (item, head, level): 2 block columns x 8 points x 8 B
+
+// per-level shared-memory region capacity in texels (64 B each) for the tiled gather
+// (227 KB - LV x 16 KB record regions - 16 KB partial sums)
+template <int LV>
+__host__ __device__ constexpr int region_cap(int l) {
+  return LV == 1 ? (l == 0 ? 3072 : 0)
+       : LV == 2 ? (l == 0 ? 1856 : l == 1 ? 960 : 0)
+       : LV == 3 ? (l == 0 ? 1408 : l == 1 ? 704 : l == 2 ? 480 : 0)
+                 : (l == 0 ? 1152 : l == 1 ? 608 : l == 2 ? 384 : l == 3 ? 192 : 0);
 }
 
-// ------------------------------------------------------------------ projection + compaction
+struct GatherWs {
+  int* counts;        // [BV]            in-view items per (frame, view)       (zeroed per call)
+  int* hist;          // [keys]          items per key                          (zeroed per call)
+  int* ctrs;          // [8]             0 chunks, 1 in-view items, 2 unit cursor, 3 direct units (zeroed)
+  int* key_off;       // [keys]
+  int* key_chunk0;    // [keys + 1]
+  int* item_key;      // [items]
+  int* item_rank;     // [items]
+  int* sorted;        // [items]
+  int4* chunks;       // [max_chunks]    {first, count, frame-view, key}
+  int4* bbox;         // [max_chunks * 8 * LV]   {x0, y0, width, height} texels
+  int* direct_list;   // [max_chunks * 8]
+  uint8_t* direct_flag;  // [max_chunks * 8]
+  uint2* params;      // [8 heads][LV][items][2 block columns][8 slots]   {x0 | y0 << 16, half2(w_top, w_bottom)}
+  int keys, kx, ky, max_chunks;
+  int64_t items;
+};
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// Lays the workspace out; returns the total size in bytes (base may be null for the size query).
+static int64_t make_ws(const MvgSampleParams& p, void* base, GatherWs* w) {
+  const int64_t BV = static_cast<int64_t>(p.batch) * p.views;
+  const int64_t items = BV * p.points;
+  const int kx = (p.level_w[0] + kCore - 1) / kCore, ky = (p.level_h[0] + kCore - 1) / kCore;
+  const int64_t keys = BV * kx * ky;
+  const int64_t max_chunks = items / kChunk + keys + 1;
+  uint8_t* b = static_cast<uint8_t*>(base);
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { int64_t o = off; off = align_up(off + bytes, 256); return b ? b + o : nullptr; };
+  w->counts = reinterpret_cast<int*>(take(4 * (BV + keys + 8)));        // counts | hist | ctrs: one memset
+  w->hist = w->counts ? w->counts + BV : nullptr;
+  w->ctrs = w->counts ? w->hist + keys : nullptr;
+  w->key_off = reinterpret_cast<int*>(take(4 * keys));
+  w->key_chunk0 = reinterpret_cast<int*>(take(4 * (keys + 1)));
+  w->item_key = reinterpret_cast<int*>(take(4 * items));
+  w->item_rank = reinterpret_cast<int*>(take(4 * items));
+  w->sorted = reinterpret_cast<int*>(take(4 * items));
+  w->chunks = reinterpret_cast<int4*>(take(16 * max_chunks));
+  w->bbox = reinterpret_cast<int4*>(take(16 * max_chunks * kHeads * p.num_levels));
+  w->direct_list = reinterpret_cast<int*>(take(4 * max_chunks * kHeads));
+  w->direct_flag = reinterpret_cast<uint8_t*>(take(max_chunks * kHeads));
+  w->params = reinterpret_cast<uint2*>(take(8 * items * kHeads * p.num_levels * 16));
+  w->keys = static_cast<int>(keys);
+  w->kx = kx;
+  w->ky = ky;
+  w->max_chunks = static_cast<int>(max_chunks);
+  w->items = items;
+  return off;
+}
+
+__device__ __forceinline__ int key_of(float rx, float ry, int bv, const MvgSampleParams& prm, int kx, int ky) {
+  // rx, ry: normalised [0, 1] image coordinates (any monotone cell assignment works: binning only)
+  const int W0 = prm.level_w[0], H0 = prm.level_h[0];
+  const int tx = min(max(static_cast<int>(rx * static_cast<float>(W0)), 0), W0 - 1) / kCore;
+  const int ty = min(max(static_cast<int>(ry * static_cast<float>(H0)), 0), H0 - 1) / kCore;
+  return (bv * ky + ty) * kx + tx;
+}
+
+// rank of this lane's item inside its key: one atomic per distinct key per warp
+__device__ __forceinline__ int key_rank(int* hist, int key, uint32_t active) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t peers = __match_any_sync(active, key);
+  const int leader = __ffs(peers) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(hist + key, __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  return base + __popc(peers & ((1u << lane) - 1u));
+}
+
+// ------------------------------------------------------------------ projection + binning
 // One block = 256 consecutive points of ONE (frame, view) pair bv = blockIdx.y.
-// ws[bv] = number of in-view points of that pair (zeroed by the host wrapper before the launch),
-// ws[hdr + bv*N ...] = their flat item indices bv*N + n, ordered inside each 256-point block
-// (hdr = B*V rounded up to a multiple of 4).
 __global__ void __launch_bounds__(kPcThreads)
-project_compact_kernel(const float* __restrict__ ref3d, const MvgCamera* __restrict__ cams,
-                       const MvgSampleParams prm, float* __restrict__ ref2d_out,
-                       uint8_t* __restrict__ bounding_out, __nv_bfloat16* __restrict__ sampled,
-                       int* __restrict__ ws) {
-  __shared__ int warp_cnt[kPcThreads / 32];
-  __shared__ int block_base;
+project_bin_kernel(const float* __restrict__ ref3d, const MvgCamera* __restrict__ cams,
+                   const MvgSampleParams prm, float* __restrict__ ref2d_out,
+                   uint8_t* __restrict__ bounding_out, __nv_bfloat16* __restrict__ sampled,
+                   const GatherWs ws) {
   const int N = prm.points, V = prm.views;
   const int bv = blockIdx.y;
   const int n = blockIdx.x * kPcThreads + threadIdx.x;
   const int64_t item = static_cast<int64_t>(bv) * N + n;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   bool inb = false;
+  float rx = 0.f, ry = 0.f;
   if (n < N) {
     const int b = bv / V;
     const MvgCamera* cam = cams + bv;   // (B,V) row-major == item / N
@@ -149,11 +184,11 @@ project_compact_kernel(const float* __restrict__ ref3d, const MvgCamera* __restr
     py = fminf(fmaxf(py, -1.f), cam->clamp_max);
     const float ax = fadd(fadd(fmul(px, cam->aff[0]), fmul(py, cam->aff[1])), cam->aff[2]);
     const float ay = fadd(fadd(fmul(px, cam->aff[3]), fmul(py, cam->aff[4])), cam->aff[5]);
-    *reinterpret_cast<float2*>(ref2d_out + 2 * item) =
-        make_float2(fdiv(ax, prm.img_w), fdiv(ay, prm.img_h));
+    rx = fdiv(ax, prm.img_w);
+    ry = fdiv(ay, prm.img_h);
+    *reinterpret_cast<float2*>(ref2d_out + 2 * item) = make_float2(rx, ry);
     bounding_out[item] = inb ? 1 : 0;
   }
-  const uint32_t in_mask = __ballot_sync(0xffffffffu, inb);
   // out-of-view rows of `sampled` are defined (zeros); a warp writes one 512-byte row at a time
   uint32_t out_mask = __ballot_sync(0xffffffffu, n < N && !inb);
   const int64_t item0 = item - lane;
@@ -162,275 +197,636 @@ project_compact_kernel(const float* __restrict__ ref3d, const MvgCamera* __restr
     out_mask &= out_mask - 1;
     reinterpret_cast<uint4*>(sampled + (item0 + src) * 256)[lane] = make_uint4(0u, 0u, 0u, 0u);
   }
-  if (lane == 0) warp_cnt[warp] = __popc(in_mask);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int s = 0;
-#pragma unroll
-    for (int w = 0; w < kPcThreads / 32; ++w) {
-      const int c = warp_cnt[w];
-      warp_cnt[w] = s;
-      s += c;
-    }
-    block_base = s > 0 ? atomicAdd(ws + bv, s) : 0;
-  }
-  __syncthreads();
+  const uint32_t active = __ballot_sync(0xffffffffu, inb);
   if (inb) {
-    const int pos = block_base + warp_cnt[warp] + __popc(in_mask & ((1u << lane) - 1u));
-    const int hdr = (prm.batch * V + 3) & ~3;
-    ws[hdr + static_cast<int64_t>(bv) * N + pos] = static_cast<int>(item);
+    const int key = key_of(rx, ry, bv, prm, ws.kx, ws.ky);
+    ws.item_key[item] = key;
+    ws.item_rank[item] = key_rank(ws.hist, key, active);
+  } else if (n < N) {
+    ws.item_key[item] = -1;
   }
 }
 
-// ------------------------------------------------------------------ gather
-template <int LV> struct WarpScratch {
+// ProjAttn.forward entry: the per-level reference points are given, every item is gathered.
+__global__ void __launch_bounds__(kPcThreads)
+bin_refl_kernel(const float* __restrict__ refl_in, const MvgSampleParams prm, const GatherWs ws) {
+  const int N = prm.points;
+  const int bv = blockIdx.y;
+  const int n = blockIdx.x * kPcThreads + threadIdx.x;
+  const int64_t item = static_cast<int64_t>(bv) * N + n;
+  const bool ok = n < N;
+  const uint32_t active = __ballot_sync(0xffffffffu, ok);
+  if (ok) {
+    const float W0 = static_cast<float>(prm.level_w[0]), H0 = static_cast<float>(prm.level_h[0]);
+    const float rx = __ldg(refl_in + item * prm.num_levels * 2) * (W0 - 1.f) / W0;
+    const float ry = __ldg(refl_in + item * prm.num_levels * 2 + 1) * (H0 - 1.f) / H0;
+    const int key = key_of(rx, ry, bv, prm, ws.kx, ws.ky);
+    ws.item_key[item] = key;
+    ws.item_rank[item] = key_rank(ws.hist, key, active);
+  }
+}
+
+// ------------------------------------------------------------------ key offsets + chunk table
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();                       // warp_sums may still be read from the previous call
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int s = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    warp_sums[lane] = s;                 // inclusive over warps
+  }
+  __syncthreads();
+  *total = warp_sums[kScanThreads / 32 - 1];
+  return inc - v + (warp > 0 ? warp_sums[warp - 1] : 0);
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+bin_scan_kernel(const GatherWs ws, int cells_per_bv) {
+  __shared__ int warp_sums[32];
+  int carry_items = 0, carry_chunks = 0;
+  for (int base = 0; base < ws.keys; base += kScanThreads) {
+    const int k = base + threadIdx.x;
+    const int cnt = k < ws.keys ? ws.hist[k] : 0;
+    const int nch = (cnt + kChunk - 1) / kChunk;
+    int tot_i, tot_c;
+    const int ex_i = block_exclusive_scan(cnt, warp_sums, &tot_i);
+    const int ex_c = block_exclusive_scan(nch, warp_sums, &tot_c);
+    if (k < ws.keys) {
+      ws.key_off[k] = carry_items + ex_i;
+      ws.key_chunk0[k] = carry_chunks + ex_c;
+      if (cnt > 0) atomicAdd(ws.counts + k / cells_per_bv, cnt);
+    }
+    carry_items += tot_i;
+    carry_chunks += tot_c;
+  }
+  if (threadIdx.x == 0) {
+    ws.key_chunk0[ws.keys] = carry_chunks;
+    ws.ctrs[0] = carry_chunks;
+    ws.ctrs[1] = carry_items;
+  }
+  __syncthreads();
+  // chunk table: chunk c belongs to the last key whose first chunk is <= c (binary search)
+  for (int c = threadIdx.x; c < carry_chunks; c += kScanThreads) {
+    int lo = 0, hi = ws.keys;            // key_chunk0[lo] <= c < key_chunk0[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (ws.key_chunk0[mid] <= c) lo = mid; else hi = mid;
+    }
+    // skip empty keys that share the same first chunk: take the LAST key with key_chunk0 <= c
+    const int j = c - ws.key_chunk0[lo];
+    const int cnt = ws.hist[lo];
+    const int nch = (cnt + kChunk - 1) / kChunk;
+    const int sz = (cnt + nch - 1) / nch;              // the key's items split evenly over its chunks
+    ws.chunks[c] = make_int4(ws.key_off[lo] + j * sz, min(sz, cnt - j * sz), lo / cells_per_bv, lo);
+  }
+}
+
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const GatherWs ws) {
+  const int64_t item = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (item >= ws.items) return;
+  const int key = ws.item_key[item];
+  if (key >= 0) ws.sorted[ws.key_off[key] + ws.item_rank[item]] = static_cast<int>(item);
+}
+
+// ------------------------------------------------------------------ per-sample parameters
+template <int LV> struct ParamScratch {
   float proj[LV][kQP];                    // per pyramid level: Linear outputs (offsets | logits)
-  float4 cw[LV * 8 * kHeads];             // [sample][head]: weights * attention as {w00, w10, w01, w11}
-                                          // (block column dx = 0 pair, then dx = 1 pair)
-  int base[LV * 8 * kHeads];              // [sample][head]: 16-byte offset of the clamped 2x2 block
+};
+
+__device__ __forceinline__ void fma8_f16(float (&acc)[8], const uint4& c, float w) {
+  const __half2* h = reinterpret_cast<const __half2*>(&c);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
+    acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
+  }
+}
+
+template <int LV>
+__global__ void __launch_bounds__(kPWarps * 32, 2)
+sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ qproj, const MvgSampleParams prm,
+                     const float* __restrict__ ref2d, const float* __restrict__ refl_in, const GatherWs ws) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  ParamScratch<LV>* scratch = reinterpret_cast<ParamScratch<LV>*>(smem_dyn);        // [kPWarps]
+  __shared__ int s_bb[kHeads][LV][4];     // x0 min, y0 min, x0 max, y0 max
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ParamScratch<LV>& sc = scratch[warp];
+  const int N = prm.points, V = prm.views, B = prm.batch;
+  const int ldg = prm.ld_g;
+  constexpr int NS = LV * 8;             // samples per head
+  // phase-B ownership: head m = lane & 7, sample group sub = lane >> 3 (samples r = sub + 4 i)
+  const int m = lane & 7, sub = lane >> 3;
+  const int nchunks = ws.ctrs[0];
+  float inv_w[LV], inv_h[LV];
+#pragma unroll
+  for (int l = 0; l < LV; ++l) {
+    inv_w[l] = 1.f / static_cast<float>(prm.level_w[l]);
+    inv_h[l] = 1.f / static_cast<float>(prm.level_h[l]);
+  }
+#pragma unroll 1
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int4 ch = ws.chunks[chunk];
+    __syncthreads();                     // previous chunk's boxes were written out
+    for (int i = threadIdx.x; i < kHeads * LV * 4; i += blockDim.x)
+      (&s_bb[0][0][0])[i] = (i & 2) ? INT_MIN : INT_MAX;
+    __syncthreads();
+    int bbx0[LV], bby0[LV], bbx1[LV], bby1[LV];
+#pragma unroll
+    for (int l = 0; l < LV; ++l) { bbx0[l] = bby0[l] = INT_MAX; bbx1[l] = bby1[l] = INT_MIN; }
+#pragma unroll 1
+    for (int idx = warp; idx < ch.y; idx += kPWarps) {
+      const int pos = ch.x + idx;
+      const int64_t item = ws.sorted[pos];
+      const int n = static_cast<int>(item % N);
+      const int bv = static_cast<int>(item / N);
+      const int v = bv % V, b = bv / V;
+      const int64_t vrow0 = static_cast<int64_t>(v * B + b) * prm.spatial_size;     // first row of this view
+      const __half* grow = gmap + vrow0 * ldg;
+      float refl_x[LV], refl_y[LV];
+      if (refl_in != nullptr) {          // ProjAttn.forward entry: reference points are given
+#pragma unroll
+        for (int l = 0; l < LV; ++l) {
+          refl_x[l] = __ldg(refl_in + (item * LV + l) * 2);
+          refl_y[l] = __ldg(refl_in + (item * LV + l) * 2 + 1);
+        }
+      } else {
+        const float2 r = __ldg(reinterpret_cast<const float2*>(ref2d + 2 * item));
+#pragma unroll
+        for (int l = 0; l < LV; ++l) {   // dq_decoder.py:570-573
+          const float fW = static_cast<float>(prm.level_w[l]), fH = static_cast<float>(prm.level_h[l]);
+          refl_x[l] = fdiv(fmul(r.x, fW), fsub(fW, 1.f));
+          refl_y[l] = fdiv(fmul(r.y, fH), fsub(fH, 1.f));
+        }
+      }
+      // ---------------- phase A (a4 i+iii): sample the pre-projected map G at the reference point
+      if (lane < kQP / 8) {
+        const float* qp = qproj + (static_cast<int64_t>(b) * N + n) * kQP + lane * 8;
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(qp));
+        const float4 q1 = __ldg(reinterpret_cast<const float4*>(qp + 4));
+        uint4 cn[LV][4];
+        float cwgt[LV][4];
+#pragma unroll
+        for (int l = 0; l < LV; ++l) {
+          const int W = prm.level_w[l], H = prm.level_h[l];
+          // F.grid_sample(bilinear, zeros, align_corners=False): projattn.py:139-153
+          const float gx = fminf(fmaxf(fsub(fmul(refl_x[l], 2.f), 1.f), -1.1f), 1.1f);
+          const float gy = fminf(fmaxf(fsub(fmul(refl_y[l], 2.f), 1.f), -1.1f), 1.1f);
+          const float ix = fsub(fmul(fadd(gx, 1.f), fmul(static_cast<float>(W), 0.5f)), 0.5f);
+          const float iy = fsub(fmul(fadd(gy, 1.f), fmul(static_cast<float>(H), 0.5f)), 0.5f);
+          const float fx0 = floorf(ix), fy0 = floorf(iy);
+          const int x0 = static_cast<int>(fx0), yy0 = static_cast<int>(fy0);
+          const float we = fsub(ix, fx0), ww = fsub(1.f, we);
+          const float wso = fsub(iy, fy0), wn = fsub(1.f, wso);
+          const bool okx0 = x0 >= 0 && x0 < W, okx1 = x0 + 1 >= 0 && x0 + 1 < W;
+          const bool oky0 = yy0 >= 0 && yy0 < H, oky1 = yy0 + 1 >= 0 && yy0 + 1 < H;
+          const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
+          const int ya = min(max(yy0, 0), H - 1), yb = min(max(yy0 + 1, 0), H - 1);
+          const __half* gl = grow + static_cast<int64_t>(prm.level_start[l]) * ldg + lane * 8;
+          cn[l][0] = ldg_nc_v4(gl + static_cast<int64_t>(ya * W + xa) * ldg);
+          cn[l][1] = ldg_nc_v4(gl + static_cast<int64_t>(ya * W + xb) * ldg);
+          cn[l][2] = ldg_nc_v4(gl + static_cast<int64_t>(yb * W + xa) * ldg);
+          cn[l][3] = ldg_nc_v4(gl + static_cast<int64_t>(yb * W + xb) * ldg);
+          cwgt[l][0] = (oky0 && okx0) ? wn * ww : 0.f;
+          cwgt[l][1] = (oky0 && okx1) ? wn * we : 0.f;
+          cwgt[l][2] = (oky1 && okx0) ? wso * ww : 0.f;
+          cwgt[l][3] = (oky1 && okx1) ? wso * we : 0.f;
+        }
+#pragma unroll
+        for (int l = 0; l < LV; ++l) {
+          float r8[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) fma8_f16(r8, cn[l][c], cwgt[l][c]);
+          float4* dst = reinterpret_cast<float4*>(&sc.proj[l][lane * 8]);
+          dst[0] = make_float4(r8[0], r8[1], r8[2], r8[3]);
+          dst[1] = make_float4(r8[4], r8[5], r8[6], r8[7]);
+        }
+      }
+      __syncwarp();
+      // ---------------- phase B (a4 iv+v, a5 index path): per (head, sample) records.
+      // 4 lanes per head, lane `sub` owns samples r = sub + 4 i (level i >> 1, point sub + 4 (i & 1)).
+      {
+        float lg[NS / 4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NS / 4; ++i) {
+          const int g = m * NS + sub + 4 * i;          // flat logit index after the `.view`
+          lg[i] = sc.proj[g >> 6][128 + (g & 63)];
+          mx = fmaxf(mx, lg[i]);
+        }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NS / 4; ++i) {
+          lg[i] = expf(lg[i] - mx);
+          sum += lg[i];
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+        const float inv_sum = 1.f / sum;
+#pragma unroll
+        for (int i = 0; i < NS / 4; ++i) {
+          const int r = sub + 4 * i;
+          const int l = i >> 1;                        // == r >> 3 because sub < 4 (static index)
+          const float wgt = lg[i] * inv_sum;
+          const int f = m * (NS * 2) + 2 * r;          // flat offset index after the `.view`
+          const float2 off = *reinterpret_cast<const float2*>(&sc.proj[f >> 7][f & 127]);
+          const int W = prm.level_w[l], H = prm.level_h[l];
+          const float rlx = refl_x[l], rly = refl_y[l];
+          const float fW = static_cast<float>(W), fH = static_cast<float>(H);
+          // projattn.py:186-191, then deform_im2col_cuda.cuh:291-301 and :41-93
+          // (reciprocal instead of the reference's division: the offsets come from the fp16 map,
+          //  so this path is not bit-comparable anyway; mvg_deform_forward keeps exact inputs)
+          const float loc_x = fadd(rlx, fmul(off.x, inv_w[l]));
+          const float loc_y = fadd(rly, fmul(off.y, inv_h[l]));
+          const float h_im = fsub(fmul(loc_y, fH), 0.5f);
+          const float w_im = fsub(fmul(loc_x, fW), 0.5f);
+          const bool inside = h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW;
+          const float fh = floorf(h_im), fw = floorf(w_im);
+          // a sample the reference skips keeps weight 0 and is parked on the reference point's
+          // texel, so that it does not stretch the tile box
+          const int h_low = inside ? static_cast<int>(fh) : static_cast<int>(floorf(fminf(fmaxf(fsub(fmul(rly, fH), 0.5f), 0.f), fH)));
+          const int w_low = inside ? static_cast<int>(fw) : static_cast<int>(floorf(fminf(fmaxf(fsub(fmul(rlx, fW), 0.5f), 0.f), fW)));
+          const float lh = inside ? h_im - fh : 0.f, lw = inside ? w_im - fw : 0.f;
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          // The 2x2 texel block is clamped into the level ((ha, wa) .. (ha+1, wa+1) always exist,
+          // H, W >= 2); a corner the reference skips (deform_im2col_cuda.cuh:57-80) gets weight 0
+          // and the surviving row / column moves to the block row / column that holds its texel.
+          const int ha = min(max(h_low, 0), H - 2), wa = min(max(w_low, 0), W - 2);
+          const float ry0 = h_low < 0 ? lh : (h_low > H - 2 ? 0.f : hh);
+          const float ry1 = h_low < 0 ? 0.f : (h_low > H - 2 ? hh : lh);
+          const float rx0 = w_low < 0 ? lw : (w_low > W - 2 ? 0.f : hw);
+          const float rx1 = w_low < 0 ? 0.f : (w_low > W - 2 ? hw : lw);
+          const float sw = inside ? wgt : 0.f;
+          bbx0[l] = min(bbx0[l], wa); bbx1[l] = max(bbx1[l], wa);
+          bby0[l] = min(bby0[l], ha); bby1[l] = max(bby1[l], ha);
+          const uint32_t xy = static_cast<uint32_t>(wa) | (static_cast<uint32_t>(ha) << 16);
+          // slot order inside a block column: points (q, q + 4) adjacent, so that the gather lane of
+          // quarter q reads its two records with one 16-byte load
+          uint2* rec = ws.params + ((static_cast<int64_t>(m) * LV + l) * ws.items + pos) * 16 + sub * 2 + (i & 1);
+          rec[0] = make_uint2(xy, pack_f16x2(ry0 * rx0 * sw, ry1 * rx0 * sw));      // left block column
+          rec[8] = make_uint2(xy, pack_f16x2(ry0 * rx1 * sw, ry1 * rx1 * sw));      // right block column
+        }
+      }
+      __syncwarp();   // scratch is reused by the next item
+    }
+    // chunk-wide bounding boxes of the (head, level) sample blocks
+#pragma unroll
+    for (int l = 0; l < LV; ++l) {
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        bbx0[l] = min(bbx0[l], __shfl_xor_sync(0xffffffffu, bbx0[l], o));
+        bby0[l] = min(bby0[l], __shfl_xor_sync(0xffffffffu, bby0[l], o));
+        bbx1[l] = max(bbx1[l], __shfl_xor_sync(0xffffffffu, bbx1[l], o));
+        bby1[l] = max(bby1[l], __shfl_xor_sync(0xffffffffu, bby1[l], o));
+      }
+      if (sub == 0 && bbx0[l] != INT_MAX) {
+        atomicMin(&s_bb[m][l][0], bbx0[l]); atomicMin(&s_bb[m][l][1], bby0[l]);
+        atomicMax(&s_bb[m][l][2], bbx1[l]); atomicMax(&s_bb[m][l][3], bby1[l]);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < kHeads) {
+      const int h = threadIdx.x;
+      bool fits = true;
+#pragma unroll
+      for (int l = 0; l < LV; ++l) {
+        const int x0 = s_bb[h][l][0], y0 = s_bb[h][l][1];
+        const int bw = s_bb[h][l][2] + 2 - x0, bh = s_bb[h][l][3] + 2 - y0;
+        ws.bbox[(static_cast<int64_t>(chunk) * kHeads + h) * LV + l] = make_int4(x0, y0, bw, bh);
+        fits = fits && bw * bh <= region_cap<LV>(l);
+      }
+      ws.direct_flag[chunk * kHeads + h] = fits ? 0 : 1;
+      if (!fits) ws.direct_list[atomicAdd(ws.ctrs + 3, 1)] = chunk * kHeads + h;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ the gather proper
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Two samples of one (item, head, level): lane = quarter q * 8 + block column dx * 4 + 16-byte chunk c
+// gathers, for sample points q and q + 4, the top and bottom texel rows of its block column and blends
+// them in packed fp16; the 8 (q, dx) roles are then summed with a transposing butterfly, after which
+// lane holds channel (lane & 3) * 8 + bit4 * 4 + bit3 * 2 + bit2 of the head.
+template <bool kShared>
+__device__ __forceinline__ float gather_two(const uint2 r0, const uint2 r1, uint32_t sbase, const uint4* gbase,
+                                            int bw, int bx0, int by0, int lane) {
+  __half2 acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = __float2half2_rn(0.f);
+  const int lc = lane & 7;               // dx * 4 + c: 16-byte unit inside the 128-byte corner pair
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const uint2 r = s ? r1 : r0;
+    const int x0 = static_cast<int>(r.x & 0xffffu), y0 = static_cast<int>(r.x >> 16);
+    const int t = (y0 - by0) * bw + (x0 - bx0);
+    uint4 top, bot;
+    if (kShared) {
+      const uint32_t a = sbase + static_cast<uint32_t>(t * 4 + lc) * 16u;
+      top = lds128(a);
+      bot = lds128(a + static_cast<uint32_t>(bw) * 64u);
+    } else {
+      const uint4* p = gbase + static_cast<int64_t>(t) * 4 + lc;
+      top = __ldg(p);
+      bot = __ldg(p + bw * 4);
+    }
+    const __half2 w = *reinterpret_cast<const __half2*>(&r.y);
+    const __half2 wt = __low2half2(w), wb = __high2half2(w);
+    const __half2* th = reinterpret_cast<const __half2*>(&top);
+    const __half2* bh = reinterpret_cast<const __half2*>(&bot);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      acc[k] = __hfma2(wt, th[k], acc[k]);
+      acc[k] = __hfma2(wb, bh[k], acc[k]);
+    }
+  }
+  auto xchg = [](const __half2 v, int o) {
+    const uint32_t u = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<const uint32_t*>(&v), o);
+    return *reinterpret_cast<const __half2*>(&u);
+  };
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  __half2 k0 = b4 ? acc[2] : acc[0], k1 = b4 ? acc[3] : acc[1];
+  k0 = __hadd2(k0, xchg(b4 ? acc[0] : acc[2], 16));
+  k1 = __hadd2(k1, xchg(b4 ? acc[1] : acc[3], 16));
+  __half2 kk = b3 ? k1 : k0;
+  kk = __hadd2(kk, xchg(b3 ? k0 : k1, 8));
+  kk = __hadd2(kk, xchg(kk, 4));
+  return b2 ? __high2float(kk) : __low2float(kk);
+}
+__device__ __forceinline__ int lane_channel(int lane) {
+  return (lane & 3) * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+}
+
+struct __align__(16) UnitDesc {
+  int first, count, head, unit;
+  int4 box[MVG_MAX_LEVELS];
 };
 
 template <int LV>
-__global__ void __launch_bounds__(kWarps * 32, 1)
-gather_kernel(const __nv_bfloat16* __restrict__ value_hm, const __nv_bfloat16* __restrict__ gmap,
-              const float* __restrict__ qproj, const MvgSampleParams prm, __nv_bfloat16* __restrict__ sampled,
-              const float* __restrict__ ref2d, const float* __restrict__ refl_in,
-              const int* __restrict__ ws) {
-  extern __shared__ __align__(16) uint8_t smem_dyn[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  WarpScratch<LV>& sc = reinterpret_cast<WarpScratch<LV>*>(smem_dyn)[warp];
-  const int N = prm.points, V = prm.views, B = prm.batch;
-  const int ldg = prm.ld_g;            // row stride of the offset / logit map G, elements
-  constexpr int NS = LV * 8;           // samples per head
-  // phase-B ownership: head m = lane & 7, sample group sub = lane >> 3 (samples r = sub + 4 i):
-  // a quarter-warp then stores 8 consecutive float4 slots [r][0..7] (conflict-free).
-  // phase-C ownership: lane = hsel * 8 + dx * 4 + chunk.  The value tensor is head-major
-  // ([head][row][32 ch], 64 B per (texel, head)), so the two horizontal corners of a bilinear
-  // footprint are 128 contiguous bytes: the 8 lanes (dx, chunk) of a quarter-warp fetch them with
-  // ONE L1 request, and one LDG.128 covers a block row of 4 heads (hsel).  Two passes (hg) cover
-  // the 8 heads, two loads (block rows dy) the footprint.
-  const int m = lane & 7, sub = lane >> 3;
-  const int hsel = lane >> 3, dxl = (lane >> 2) & 1, subc = lane & 3;
-  // identity B fragment of mma.m16n8k8 (tensor-pipe unpack option): B[k][n] = (k == n), lane
-  // (g, t) = (lane >> 2, lane & 3) holds k = 2t, 2t+1 of column n = g as a bf16 pair
-  const uint32_t b_ident = (lane >> 2) == 2 * (lane & 3) ? 0x00003F80u
-                                                         : ((lane >> 2) == 2 * (lane & 3) + 1 ? 0x3F800000u : 0u);
-  // View-major sweep: for every (frame, view) pair in turn, each CTA takes an equal slice of that
-  // pair's in-view list and its 16 warps walk it together (warp w: first + w, first + w + 16, ...).
-  // All SMs therefore read ONE view's value / G maps at a time (36 MB, L2-resident) instead of all
-  // views at once (180 MB > 126 MB L2), and inside a slice an SM still works on ~one person's
-  // joints, whose overlapping footprints share its L1.
-  const int BV = B * V;
-  const int hdr = (BV + 3) & ~3;
-#pragma unroll 1
-  for (int bvi = 0; bvi < BV; ++bvi) {
-  const int cnt = ws != nullptr ? __ldg(ws + bvi) : N;
-  const int first = static_cast<int>(static_cast<int64_t>(cnt) * blockIdx.x / gridDim.x);
-  const int last = static_cast<int>(static_cast<int64_t>(cnt) * (blockIdx.x + 1) / gridDim.x);
-#pragma unroll 1
-  for (int idx = first + warp; idx < last; idx += kWarps) {
-    const int64_t item = ws != nullptr ? static_cast<int64_t>(__ldg(ws + hdr + static_cast<int64_t>(bvi) * N + idx))
-                                       : static_cast<int64_t>(bvi) * N + idx;
-    const int64_t out_idx = item;
-    const int n = static_cast<int>(item % N);
-    const int bv = static_cast<int>(item / N);
-    const int v = bv % V, b = bv / V;
-    const int64_t vrow0 = static_cast<int64_t>(v * B + b) * prm.spatial_size;     // first row of this view
-    const __nv_bfloat16* grow = gmap + vrow0 * ldg;
-    float refl_x[LV], refl_y[LV];
-    if (refl_in != nullptr) {          // ProjAttn.forward entry: reference points are given
-#pragma unroll
-      for (int l = 0; l < LV; ++l) {
-        refl_x[l] = __ldg(refl_in + (item * LV + l) * 2);
-        refl_y[l] = __ldg(refl_in + (item * LV + l) * 2 + 1);
-      }
-    } else {
-      const float2 r = __ldg(reinterpret_cast<const float2*>(ref2d + 2 * item));
-#pragma unroll
-      for (int l = 0; l < LV; ++l) {   // dq_decoder.py:570-573
-        const float fW = static_cast<float>(prm.level_w[l]), fH = static_cast<float>(prm.level_h[l]);
-        refl_x[l] = fdiv(fmul(r.x, fW), fsub(fW, 1.f));
-        refl_y[l] = fdiv(fmul(r.y, fH), fsub(fH, 1.f));
-      }
-    }
+struct TileSmem {
+  static constexpr int kTexels = region_cap<LV>(0) + region_cap<LV>(1) + region_cap<LV>(2) + region_cap<LV>(3);
+  static constexpr int kRecOff = kTexels * 64;                       // LV record regions of kChunk x 128 B
+  static constexpr int kPartialOff = kRecOff + LV * kChunk * kRecBytes;
+  static constexpr int kDescOff = kPartialOff + kChunk * 32 * 4;
+  static constexpr int kBytes = kDescOff + 2 * static_cast<int>(sizeof(UnitDesc)) + 128;
+};
 
-    float inv_w[LV], inv_h[LV];
+template <int LV>
+__global__ void __launch_bounds__((kGWarps + 1) * 32, 1)
+gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams prm,
+                    __nv_bfloat16* __restrict__ sampled, const GatherWs ws) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  float* partial = reinterpret_cast<float*>(smem + TileSmem<LV>::kPartialOff);       // [kChunk][32]
+  UnitDesc* sdesc = reinterpret_cast<UnitDesc*>(smem + TileSmem<LV>::kDescOff);      // [2]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sdesc + 2);                           // [LV]
+  uint64_t* empty = full + MVG_MAX_LEVELS;                                           // [LV]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t region[LV], recs[LV];
+  {
+    uint32_t a = smem_u32(smem);
 #pragma unroll
     for (int l = 0; l < LV; ++l) {
-      inv_w[l] = 1.f / static_cast<float>(prm.level_w[l]);
-      inv_h[l] = 1.f / static_cast<float>(prm.level_h[l]);
+      region[l] = a;
+      a += region_cap<LV>(l) * 64;
+      recs[l] = smem_u32(smem) + TileSmem<LV>::kRecOff + l * kChunk * kRecBytes;
     }
-    // ---------------- phase A (a4 i+iii): sample the pre-projected map G at the reference point
-    if (lane < kQP / 8) {
-      const float* qp = qproj + (static_cast<int64_t>(b) * N + n) * kQP + lane * 8;
-      const float4 q0 = __ldg(reinterpret_cast<const float4*>(qp));
-      const float4 q1 = __ldg(reinterpret_cast<const float4*>(qp + 4));
-      const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-      uint4 cn[LV][4];
-      float cwgt[LV][4];
-#pragma unroll
-      for (int l = 0; l < LV; ++l) {
-        const int W = prm.level_w[l], H = prm.level_h[l];
-        // F.grid_sample(bilinear, zeros, align_corners=False): projattn.py:139-153
-        const float gx = fminf(fmaxf(fsub(fmul(refl_x[l], 2.f), 1.f), -1.1f), 1.1f);
-        const float gy = fminf(fmaxf(fsub(fmul(refl_y[l], 2.f), 1.f), -1.1f), 1.1f);
-        const float ix = fsub(fmul(fadd(gx, 1.f), fmul(static_cast<float>(W), 0.5f)), 0.5f);
-        const float iy = fsub(fmul(fadd(gy, 1.f), fmul(static_cast<float>(H), 0.5f)), 0.5f);
-        const float fx0 = floorf(ix), fy0 = floorf(iy);
-        const int x0 = static_cast<int>(fx0), yy0 = static_cast<int>(fy0);
-        const float we = fsub(ix, fx0), ww = fsub(1.f, we);
-        const float ws = fsub(iy, fy0), wn = fsub(1.f, ws);
-        const bool okx0 = x0 >= 0 && x0 < W, okx1 = x0 + 1 >= 0 && x0 + 1 < W;
-        const bool oky0 = yy0 >= 0 && yy0 < H, oky1 = yy0 + 1 >= 0 && yy0 + 1 < H;
-        const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
-        const int ya = min(max(yy0, 0), H - 1), yb = min(max(yy0 + 1, 0), H - 1);
-        const __nv_bfloat16* gl = grow + static_cast<int64_t>(prm.level_start[l]) * ldg + lane * 8;
-        cn[l][0] = ldg_nc_v4(gl + static_cast<int64_t>(ya * W + xa) * ldg);
-        cn[l][1] = ldg_nc_v4(gl + static_cast<int64_t>(ya * W + xb) * ldg);
-        cn[l][2] = ldg_nc_v4(gl + static_cast<int64_t>(yb * W + xa) * ldg);
-        cn[l][3] = ldg_nc_v4(gl + static_cast<int64_t>(yb * W + xb) * ldg);
-        cwgt[l][0] = (oky0 && okx0) ? wn * ww : 0.f;
-        cwgt[l][1] = (oky0 && okx1) ? wn * we : 0.f;
-        cwgt[l][2] = (oky1 && okx0) ? ws * ww : 0.f;
-        cwgt[l][3] = (oky1 && okx1) ? ws * we : 0.f;
-      }
-#pragma unroll
-      for (int l = 0; l < LV; ++l) {
-        uint64_t a2[4] = {pack2(qv[0], qv[1]), pack2(qv[2], qv[3]), pack2(qv[4], qv[5]), pack2(qv[6], qv[7])};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) fma2_corner(a2, cn[l][c], cwgt[l][c]);
-        float r8[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) unpack2(a2[i], r8[2 * i], r8[2 * i + 1]);
-        float4* dst = reinterpret_cast<float4*>(&sc.proj[l][lane * 8]);
-        dst[0] = make_float4(r8[0], r8[1], r8[2], r8[3]);
-        dst[1] = make_float4(r8[4], r8[5], r8[6], r8[7]);
-      }
-    }
-    __syncwarp();
-
-    // ---------------- phase B (a4 iv+v, a5 index path): per (head, sample) parameters.
-    // 4 lanes per head, lane `sub` owns samples r = sub + 4 i.
-    {
-      float lg[NS / 4];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < NS / 4; ++i) {
-        const int g = m * NS + sub + 4 * i;          // flat logit index after the `.view`
-        lg[i] = sc.proj[g >> 6][128 + (g & 63)];
-        mx = fmaxf(mx, lg[i]);
-      }
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < NS / 4; ++i) {
-        lg[i] = expf(lg[i] - mx);
-        sum += lg[i];
-      }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 8);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-      const float inv_sum = 1.f / sum;
-#pragma unroll
-      for (int i = 0; i < NS / 4; ++i) {
-        const int r = sub + 4 * i;
-        const int l = i >> 1;                        // == r >> 3 because sub < 4 (static index)
-        const float wgt = lg[i] * inv_sum;
-        const int f = m * (NS * 2) + 2 * r;          // flat offset index after the `.view`
-        const float2 off = *reinterpret_cast<const float2*>(&sc.proj[f >> 7][f & 127]);
-        const int W = prm.level_w[l], H = prm.level_h[l], start = prm.level_start[l];
-        const float rlx = refl_x[l], rly = refl_y[l];
-        const float fW = static_cast<float>(W), fH = static_cast<float>(H);
-        // projattn.py:186-191, then deform_im2col_cuda.cuh:291-301 and :41-93
-        // (reciprocal instead of the reference's division: the offsets come from the bf16 map,
-        //  so this path is not bit-comparable anyway; mvg_deform_forward keeps exact inputs)
-        const float loc_x = fadd(rlx, fmul(off.x, inv_w[l]));
-        const float loc_y = fadd(rly, fmul(off.y, inv_h[l]));
-        const float h_im = fsub(fmul(loc_y, fH), 0.5f);
-        const float w_im = fsub(fmul(loc_x, fW), 0.5f);
-        const bool inside = h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW;
-        const float fh = floorf(h_im), fw = floorf(w_im);
-        const int h_low = inside ? static_cast<int>(fh) : 0;
-        const int w_low = inside ? static_cast<int>(fw) : 0;
-        const float lh = inside ? h_im - fh : 0.f, lw = inside ? w_im - fw : 0.f;
-        const float hh = 1.f - lh, hw = 1.f - lw;
-        // The 2x2 texel block is clamped into the level ((ha, wa) .. (ha+1, wa+1) always exist,
-        // H, W >= 2); a corner the reference skips (deform_im2col_cuda.cuh:57-80) gets weight 0
-        // and the surviving row / column moves to the block row / column that holds its texel.
-        const int ha = min(max(h_low, 0), H - 2), wa = min(max(w_low, 0), W - 2);
-        const float ry0 = h_low < 0 ? lh : (h_low > H - 2 ? 0.f : hh);
-        const float ry1 = h_low < 0 ? 0.f : (h_low > H - 2 ? hh : lh);
-        const float rx0 = w_low < 0 ? lw : (w_low > W - 2 ? 0.f : hw);
-        const float rx1 = w_low < 0 ? 0.f : (w_low > W - 2 ? hw : lw);
-        const float sw = inside ? wgt : 0.f;
-        sc.cw[r * kHeads + m] = make_float4(ry0 * rx0 * sw, ry1 * rx0 * sw, ry0 * rx1 * sw, ry1 * rx1 * sw);
-        sc.base[r * kHeads + m] = (start + ha * W + wa) * 4;      // 16-byte units, 64 B per (texel, head)
-      }
-    }
-    __syncwarp();
-
-    // ---------------- phase C (a5): gather 2 block rows x NS samples x 2 head groups
-    uint64_t acc2[2][4];                             // [head group][8 fp32 channels as 4 pairs]
-#pragma unroll
-    for (int hg = 0; hg < 2; ++hg) acc2[hg][0] = acc2[hg][1] = acc2[hg][2] = acc2[hg][3] = 0ull;
-    const uint4* vl[2];
-#pragma unroll
-    for (int hg = 0; hg < 2; ++hg)
-      vl[hg] = reinterpret_cast<const uint4*>(value_hm + (static_cast<int64_t>(hg * 4 + hsel) * prm.value_head_stride +
-                                                          vrow0 * 32)) + dxl * 4 + subc;
-#pragma unroll
-    for (int l = 0; l < LV; ++l) {
-      const uint32_t rowstep16 = static_cast<uint32_t>(prm.level_w[l]) * 4u;
-#pragma unroll kPsUnroll
-      for (int p = 0; p < 8; ++p) {
-        const int r = l * 8 + p;
-#pragma unroll
-        for (int hg = 0; hg < 2; ++hg) {
-          // this lane's block column: (top, bottom) weights
-          const float2 cwv = reinterpret_cast<const float2*>(&sc.cw[r * kHeads + hg * 4 + hsel])[dxl];
-          const uint4* p0 = vl[hg] + static_cast<uint32_t>(sc.base[r * kHeads + hg * 4 + hsel]);
-          const uint4 ct = __ldg(p0);
-          const uint4 cb = __ldg(p0 + rowstep16);
-          fma_corner(acc2[hg], ct, cwv.x, b_ident);
-          fma_corner(acc2[hg], cb, cwv.y, b_ident);
-        }
-      }
-    }
-    // left + right block columns: lanes (dx = 0) and (dx = 1) hold the two halves of every sum;
-    // afterwards lane (hsel, dx, chunk) owns head 4 dx + hsel
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float a0, a1, b0, b1;
-      unpack2(acc2[0][i], a0, a1);
-      unpack2(acc2[1][i], b0, b1);
-      a0 += __shfl_xor_sync(0xffffffffu, a0, 4); a1 += __shfl_xor_sync(0xffffffffu, a1, 4);
-      b0 += __shfl_xor_sync(0xffffffffu, b0, 4); b1 += __shfl_xor_sync(0xffffffffu, b1, 4);
-      acc[2 * i] = dxl ? b0 : a0;
-      acc[2 * i + 1] = dxl ? b1 : a1;
-    }
-    uint4 o;
-    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-    *reinterpret_cast<uint4*>(sampled + out_idx * 256 + (dxl * 4 + hsel) * 32 + subc * 8) = o;
-    __syncwarp();   // scratch is reused by the next item
   }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int l = 0; l < LV; ++l) { mbar_init(&full[l], 1); mbar_init(&empty[l], kGWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int n_units = ws.ctrs[0] * kHeads;
+  const int V = prm.views, B = prm.batch;
+
+  if (warp == kGWarps) {
+    // ===================== producer: unit descriptors, tile rows, record blocks =====================
+    // The next unit's metadata (work-queue ticket, chunk, boxes) is fetched right after this unit's
+    // level-0 copies are issued, so its global-memory latency hides behind the copies in flight.
+    int unit = -1;
+    int4 ch = make_int4(0, 0, 0, 0), box[LV];
+    auto fetch = [&]() {
+      for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(ws.ctrs + 2, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) { unit = -1; return; }
+        if (ws.direct_flag[u] != 0) continue;              // left to gather_direct_kernel
+        unit = u;
+        ch = ws.chunks[u / kHeads];
+#pragma unroll
+        for (int l = 0; l < LV; ++l) box[l] = ws.bbox[static_cast<int64_t>(u) * LV + l];
+        return;
+      }
+    };
+    fetch();
+    uint32_t seq = 0;
+    for (;;) {
+      const uint32_t par = seq & 1u;
+      mbar_wait(&empty[0], par ^ 1u);      // level 0 of unit seq-1 consumed => descriptor slot (seq & 1) is free
+      UnitDesc* d = &sdesc[par];
+      if (unit < 0) {
+        if (lane == 0) { d->count = -1; mbar_arrive(&full[0]); }
+        break;
+      }
+      const int head = unit % kHeads;
+      const int first = ch.x, count = ch.y;
+      const int v = ch.z % V, b = ch.z / V;
+      const int64_t vrow0 = static_cast<int64_t>(v * B + b) * prm.spatial_size;
+      if (lane == 0) {
+        d->first = first; d->count = count; d->head = head; d->unit = unit;
+#pragma unroll
+        for (int l = 0; l < LV; ++l) d->box[l] = box[l];
+      }
+      __syncwarp();
+      const __half* vh = value_hm + static_cast<int64_t>(head) * prm.value_head_stride;
+      const uint2* rec_src = ws.params + (static_cast<int64_t>(head) * LV * ws.items + first) * 16;
+      int4 cbox[LV];
+#pragma unroll
+      for (int l = 0; l < LV; ++l) cbox[l] = box[l];
+#pragma unroll
+      for (int l = 0; l < LV; ++l) {
+        if (l > 0) mbar_wait(&empty[l], par ^ 1u);
+        const int bw = cbox[l].z, bh = cbox[l].w;
+        const uint32_t row_bytes = static_cast<uint32_t>(bw) * 64u;
+        const uint32_t rec_bytes = static_cast<uint32_t>(count) * kRecBytes;
+        if (lane == 0) {
+          mbar_expect_tx(&full[l], row_bytes * static_cast<uint32_t>(bh) + rec_bytes);
+          bulk_g2s(recs[l], rec_src + static_cast<int64_t>(l) * ws.items * 16, rec_bytes, &full[l]);
+        }
+        __syncwarp();
+        const __half* src0 = vh + (vrow0 + prm.level_start[l] + static_cast<int64_t>(cbox[l].y) * prm.level_w[l] + cbox[l].x) * 32;
+        for (int r = lane; r < bh; r += 32)
+          bulk_g2s(region[l] + static_cast<uint32_t>(r) * row_bytes, src0 + static_cast<int64_t>(r) * prm.level_w[l] * 32,
+                   row_bytes, &full[l]);
+        if (l == 0) fetch();               // overwrites unit / ch / box: cbox, first, count, head are this unit's
+      }
+      ++seq;
+    }
+  } else {
+    // ===================== consumers: level-by-level gather =====================
+    uint32_t seq = 0;
+    const int q = lane >> 3, dx = (lane >> 2) & 1;
+    const int chn = lane_channel(lane);
+    const uint32_t rec_lane = static_cast<uint32_t>(dx * 64 + q * 16);
+    for (;;) {
+      const uint32_t par = seq & 1u;
+      mbar_wait(&full[0], par);
+      const UnitDesc* d = &sdesc[par];
+      const int count = d->count;
+      if (count < 0) break;
+      const int first = d->first, head = d->head;
+      // ids of the items this warp owns (i = warp + 16 k): lane k keeps item k's id for the final store
+      int my_item = 0;
+      if (warp + kGWarps * lane < count) my_item = __ldg(ws.sorted + first + warp + kGWarps * lane);
+#pragma unroll
+      for (int l = 0; l < LV; ++l) {
+        if (l > 0) mbar_wait(&full[l], par);
+        const int4 box = d->box[l];
+#pragma unroll 1
+        for (int i = warp, k = 0; i < count; i += kGWarps, ++k) {
+          const uint4 rc = lds128(recs[l] + static_cast<uint32_t>(i) * kRecBytes + rec_lane);
+          const float vsum = gather_two<true>(make_uint2(rc.x, rc.y), make_uint2(rc.z, rc.w), region[l], nullptr,
+                                              box.z, box.x, box.y, lane);
+          float* ps = partial + i * 32 + chn;
+          float tot = vsum;
+          if (l > 0) tot = *ps + vsum;
+          if (l + 1 < LV) *ps = tot;
+          if (l + 1 == LV) {
+            const int64_t item = __shfl_sync(0xffffffffu, my_item, k);
+            sampled[item * 256 + head * 32 + chn] = __float2bfloat16(tot);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[l]);
+      }
+      ++seq;
+    }
   }
 }
 
+// Units whose sample boxes exceed the shared-memory regions: one warp per (unit, item), same
+// arithmetic from global memory.
+template <int LV>
+__global__ void __launch_bounds__(256)
+gather_direct_kernel(const __half* __restrict__ value_hm, const MvgSampleParams prm,
+                     __nv_bfloat16* __restrict__ sampled, const GatherWs ws) {
+  const int lane = threadIdx.x & 31;
+  const int n_direct = ws.ctrs[3];
+  const int q = lane >> 3, dx = (lane >> 2) & 1;
+  const int chn = lane_channel(lane);
+  const int V = prm.views, B = prm.batch;
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  const int64_t gw = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+#pragma unroll 1
+  for (int64_t w = gw; w < static_cast<int64_t>(n_direct) * kChunk; w += warps_total) {
+    const int unit = ws.direct_list[w / kChunk];
+    const int i = static_cast<int>(w % kChunk);
+    const int chunk = unit / kHeads, head = unit % kHeads;
+    const int4 ch = ws.chunks[chunk];
+    if (i >= ch.y) continue;
+    const int v = ch.z % V, b = ch.z / V;
+    const int64_t vrow0 = static_cast<int64_t>(v * B + b) * prm.spatial_size;
+    const __half* vh = value_hm + static_cast<int64_t>(head) * prm.value_head_stride;
+    const uint2* rec = ws.params + (static_cast<int64_t>(head) * LV * ws.items + ch.x + i) * 16 + dx * 8 + q * 2;
+    float tot = 0.f;
+#pragma unroll
+    for (int l = 0; l < LV; ++l) {
+      const uint4 rc = __ldg(reinterpret_cast<const uint4*>(rec + l * ws.items * 16));
+      const uint2 c0 = make_uint2(rc.x, rc.y), c1 = make_uint2(rc.z, rc.w);
+      const uint4* gb = reinterpret_cast<const uint4*>(vh + (vrow0 + prm.level_start[l]) * 32);
+      const float vsum = gather_two<false>(c0, c1, 0u, gb, prm.level_w[l], 0, 0, lane);
+      tot = l == 0 ? vsum : tot + vsum;
+    }
+    const int64_t item = ws.sorted[ch.x + i];
+    sampled[item * 256 + head * 32 + chn] = __float2bfloat16(tot);
+  }
+}
+
+template <int LV>
+static int launch_gather(const __half* vhm, const __half* gmp, const float* qproj, const MvgSampleParams& prm,
+                         __nv_bfloat16* sp, const float* ref2d, const float* refl_in, const GatherWs& ws,
+                         cudaStream_t st) {
+  constexpr int smem = TileSmem<LV>::kBytes;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gather_tiles_kernel<LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gather_tiles, %d B): %s", smem, cudaGetErrorString(e));
+      return MVG_ELAUNCH;
+    }
+    attr_done = true;
+  }
+  constexpr int psmem = kPWarps * static_cast<int>(sizeof(ParamScratch<LV>));
+  static bool pattr_done = false;
+  if (!pattr_done) {
+    cudaError_t e = cudaFuncSetAttribute(sample_params_kernel<LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(sample_params, %d B): %s", psmem, cudaGetErrorString(e));
+      return MVG_ELAUNCH;
+    }
+    pattr_done = true;
+  }
+  const int64_t chunks_bound = ws.items / kChunk + ws.keys + 1;
+  const int pgrid = static_cast<int>(chunks_bound < 2 * kNumSMs ? chunks_bound : 2 * kNumSMs);
+  sample_params_kernel<LV><<<pgrid, kPWarps * 32, psmem, st>>>(gmp, qproj, prm, ref2d, refl_in, ws);
+  int rc = check_launch("mvg_project_sample_fused(sample_params)");
+  if (rc != MVG_OK) return rc;
+  const int64_t units_bound = chunks_bound * kHeads;
+  const int ggrid = static_cast<int>(units_bound < kNumSMs ? units_bound : kNumSMs);
+  gather_tiles_kernel<LV><<<ggrid, (kGWarps + 1) * 32, smem, st>>>(vhm, prm, sp, ws);
+  rc = check_launch("mvg_project_sample_fused(gather_tiles)");
+  if (rc != MVG_OK) return rc;
+  gather_direct_kernel<LV><<<kNumSMs, 256, 0, st>>>(vhm, prm, sp, ws);
+  return check_launch("mvg_project_sample_fused(gather_direct)");
+}
+
 }  // namespace mvg
+
+extern "C" int64_t mvg_project_sample_workspace_bytes(const MvgSampleParams* prm) {
+  using namespace mvg;
+  if (prm == nullptr || prm->batch <= 0 || prm->views <= 0 || prm->points <= 0 || prm->num_levels < 1 ||
+      prm->num_levels > MVG_MAX_LEVELS)
+    return -1;
+  GatherWs w;
+  return make_ws(*prm, nullptr, &w);
+}
 
 extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, const void* value_hm,
                                         const void* gmap, const float* qproj, const MvgSampleParams* prm,
                                         void* sampled, float* ref2d, uint8_t* bounding,
                                         const float* refl_in, void* workspace, void* stream) {
   using namespace mvg;
-  MVG_REQUIRE(value_hm && gmap && qproj && prm && sampled, "mvg_project_sample_fused: null pointer");
+  MVG_REQUIRE(value_hm && gmap && qproj && prm && sampled && workspace, "mvg_project_sample_fused: null pointer");
   MVG_REQUIRE((reinterpret_cast<uintptr_t>(value_hm) & 15) == 0 && (reinterpret_cast<uintptr_t>(gmap) & 15) == 0,
               "mvg_project_sample_fused: value / G map must be 16-byte aligned");
-  MVG_REQUIRE(refl_in || (ref3d && cams && ref2d && bounding && workspace),
-              "mvg_project_sample_fused: projection inputs/outputs/workspace missing");
+  MVG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+              "mvg_project_sample_fused: workspace must be 256-byte aligned");
+  MVG_REQUIRE(refl_in || (ref3d && cams && ref2d && bounding),
+              "mvg_project_sample_fused: projection inputs/outputs missing");
   MVG_REQUIRE(prm->num_levels >= 1 && prm->num_levels <= MVG_MAX_LEVELS,
               "mvg_project_sample_fused: num_levels %d out of range", prm->num_levels);
   MVG_REQUIRE(prm->batch > 0 && prm->views > 0 && prm->points > 0, "mvg_project_sample_fused: empty shape");
@@ -442,6 +838,8 @@ extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, c
   for (int l = 0; l < prm->num_levels; ++l) {
     MVG_REQUIRE(prm->level_h[l] > 1 && prm->level_w[l] > 1 && prm->level_start[l] == s,
                 "mvg_project_sample_fused: level %d shape/start inconsistent", l);
+    MVG_REQUIRE(prm->level_h[l] < 32768 && prm->level_w[l] < 32768,
+                "mvg_project_sample_fused: level %d larger than 32767 texels per side", l);
     s += prm->level_h[l] * prm->level_w[l];
   }
   MVG_REQUIRE(s == prm->spatial_size, "mvg_project_sample_fused: spatial_size %d != sum H*W %d",
@@ -450,48 +848,39 @@ extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, c
               "mvg_project_sample_fused: per-view map too large for 32-bit texel offsets");
   const int64_t total = static_cast<int64_t>(prm->batch) * prm->views * prm->points;
   MVG_REQUIRE(total < (1ll << 31), "mvg_project_sample_fused: too many items");
-  const int64_t per_cta = kWarps * 4;   // at least ~4 items per warp before spreading further
-  int64_t want = (total + per_cta - 1) / per_cta;
-  const int grid = static_cast<int>(want < kNumSMs ? (want < 1 ? 1 : want) : kNumSMs);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GatherWs ws;
+  make_ws(*prm, workspace, &ws);
+  const int64_t BV = static_cast<int64_t>(prm->batch) * prm->views;
+  cudaError_t e = cudaMemsetAsync(ws.counts, 0, sizeof(int) * (BV + ws.keys + 8), st);
+  if (e != cudaSuccess) {
+    set_error("mvg_project_sample_fused: cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return MVG_ELAUNCH;
+  }
   const MvgCamera* cam = reinterpret_cast<const MvgCamera*>(cams);
-  const __nv_bfloat16* vhm = static_cast<const __nv_bfloat16*>(value_hm);
-  const __nv_bfloat16* gmp = static_cast<const __nv_bfloat16*>(gmap);
+  const __half* vhm = static_cast<const __half*>(value_hm);
+  const __half* gmp = static_cast<const __half*>(gmap);
   __nv_bfloat16* sp = static_cast<__nv_bfloat16*>(sampled);
-  int* ws = refl_in ? nullptr : static_cast<int*>(workspace);
-  if (ws != nullptr) {
-    const int hdr = (prm->batch * prm->views + 3) & ~3;
-    cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(int) * hdr, st);
-    if (e != cudaSuccess) {
-      set_error("mvg_project_sample_fused: cudaMemsetAsync: %s", cudaGetErrorString(e));
-      return MVG_ELAUNCH;
-    }
-    const dim3 pc_grid((prm->points + kPcThreads - 1) / kPcThreads, prm->batch * prm->views);
-    project_compact_kernel<<<pc_grid, kPcThreads, 0, st>>>(ref3d, cam, *prm, ref2d, bounding, sp, ws);
-    int rc = check_launch("mvg_project_sample_fused(project_compact)");
-    if (rc != MVG_OK) return rc;
+  const dim3 pc_grid((prm->points + kPcThreads - 1) / kPcThreads, static_cast<unsigned>(BV));
+  int rc;
+  if (refl_in == nullptr) {
+    project_bin_kernel<<<pc_grid, kPcThreads, 0, st>>>(ref3d, cam, *prm, ref2d, bounding, sp, ws);
+    rc = check_launch("mvg_project_sample_fused(project_bin)");
+  } else {
+    bin_refl_kernel<<<pc_grid, kPcThreads, 0, st>>>(refl_in, *prm, ws);
+    rc = check_launch("mvg_project_sample_fused(bin_refl)");
   }
-#define MVG_LAUNCH_PS(LV)                                                                       \
-  {                                                                                             \
-    constexpr int smem = kWarps * static_cast<int>(sizeof(WarpScratch<LV>));                    \
-    static bool attr_done = false;                                                              \
-    if (!attr_done) {                                                                           \
-      cudaError_t e = cudaFuncSetAttribute(gather_kernel<LV>,                                   \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
-      if (e != cudaSuccess) {                                                                   \
-        set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));                           \
-        return MVG_ELAUNCH;                                                                     \
-      }                                                                                         \
-      attr_done = true;                                                                         \
-    }                                                                                           \
-    gather_kernel<LV><<<grid, kWarps * 32, smem, st>>>(vhm, gmp, qproj, *prm, sp, ref2d, refl_in, ws); \
-  }
+  if (rc != MVG_OK) return rc;
+  bin_scan_kernel<<<1, kScanThreads, 0, st>>>(ws, ws.kx * ws.ky);
+  rc = check_launch("mvg_project_sample_fused(bin_scan)");
+  if (rc != MVG_OK) return rc;
+  bin_scatter_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(ws);
+  rc = check_launch("mvg_project_sample_fused(bin_scatter)");
+  if (rc != MVG_OK) return rc;
   switch (prm->num_levels) {
-    case 1: MVG_LAUNCH_PS(1) break;
-    case 2: MVG_LAUNCH_PS(2) break;
-    case 3: MVG_LAUNCH_PS(3) break;
-    default: MVG_LAUNCH_PS(4) break;
+    case 1: return launch_gather<1>(vhm, gmp, qproj, *prm, sp, ref2d, refl_in, ws, st);
+    case 2: return launch_gather<2>(vhm, gmp, qproj, *prm, sp, ref2d, refl_in, ws, st);
+    case 3: return launch_gather<3>(vhm, gmp, qproj, *prm, sp, ref2d, refl_in, ws, st);
+    default: return launch_gather<4>(vhm, gmp, qproj, *prm, sp, ref2d, refl_in, ws, st);
   }
-#undef MVG_LAUNCH_PS
-  return check_launch("mvg_project_sample_fused");
 }

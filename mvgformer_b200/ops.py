@@ -73,8 +73,9 @@ def linear_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
 def value_proj(feat_cl: torch.Tensor, w_all: torch.Tensor, b_all: Optional[torch.Tensor], layers: int):
     """The pyramid projections of `layers` decoder layers in one GEMM, in the gather's layouts.
     feat_cl (rows, S, 256) bf16; w_all (layers*448, 256) bf16 = per layer [rayconv | sampling_offsets |
-    attention_weights]; b_all (layers*448) fp32.  -> value_hm (layers*8, rows*S, 32) bf16 head-major,
-    gmap (rows*S, layers*192) bf16."""
+    attention_weights]; b_all (layers*448) fp32.  -> value_hm (layers*8, rows*S, 32) fp16 head-major,
+    gmap (rows*S, layers*192) fp16 (bf16 operands, fp32 accumulation, fp16 stores: the gather blends
+    in packed fp16)."""
     from .linear import get_backend
     M = feat_cl.shape[0] * feat_cl.shape[1]
     dev = feat_cl.device
@@ -83,12 +84,12 @@ def value_proj(feat_cl: torch.Tensor, w_all: torch.Tensor, b_all: Optional[torch
         y = torch.mm(feat_cl.reshape(M, 256), w_all.t(), out_dtype=torch.float32)
         if b_all is not None:
             y = y + b_all
-        y = y.to(torch.bfloat16).view(M, layers, 448)
+        y = y.to(torch.float16).view(M, layers, 448)
         value_hm = y[:, :, :256].reshape(M, layers * 8, 32).permute(1, 0, 2).contiguous()
         return value_hm, y[:, :, 256:].reshape(M, layers * 192).contiguous()
     lib = _lib.load()
-    value_hm = torch.empty((layers * 8, M, 32), dtype=torch.bfloat16, device=dev)
-    gmap = torch.empty((M, layers * 192), dtype=torch.bfloat16, device=dev)
+    value_hm = torch.empty((layers * 8, M, 32), dtype=torch.float16, device=dev)
+    gmap = torch.empty((M, layers * 192), dtype=torch.float16, device=dev)
     check(lib.mvg_value_proj_gemm(feat_cl.data_ptr(), w_all.data_ptr(), _lib.ptr(b_all), M, layers,
                                   value_hm.data_ptr(), gmap.data_ptr(), stream_ptr(dev)), "mvg_value_proj_gemm")
     return value_hm, gmap
@@ -116,15 +117,20 @@ def project_sample_fused(ref3d: Optional[torch.Tensor], cams: Optional[torch.Ten
     """value_hm: this layer's 8 heads of the head-major value tensor (8, rows*S, 32); gmap: this
     layer's 192 columns of G (a column slice, row stride prm.ld_g).
     -> sampled (B,V,N,256) bf16, ref2d (B,V,N,2) fp32, bounding (B,V,N) uint8, work (the int32
-    workspace, [:B*V] = in-view item counts per (frame, view); None on the ProjAttn entry)."""
+    workspace, [:B*V] = in-view item counts per (frame, view))."""
     lib = _lib.load()
     dev = value_hm.device
     B, V, N = prm.batch, prm.views, prm.points
     sampled = torch.empty((B, V, N, 256), dtype=torch.bfloat16, device=dev)
     ref2d = torch.empty((B, V, N, 2), dtype=torch.float32, device=dev)
     bounding = torch.empty((B, V, N), dtype=torch.uint8, device=dev)
-    # per-(frame, view) in-view counts + item lists; not needed on the ProjAttn entry (refl given)
-    work = None if refl is not None else torch.empty((B * V * N + B * V + 4,), dtype=torch.int32, device=dev)
+    if value_hm.dtype != torch.float16 or gmap.dtype != torch.float16:
+        raise _lib.MvgError("project_sample_fused: value_hm / gmap must be float16 (ops.value_proj output)")
+    # binning tables, per-sample records and (first B*V ints) the in-view counts per (frame, view)
+    nbytes = int(lib.mvg_project_sample_workspace_bytes(C.byref(prm)))
+    if nbytes <= 0:
+        raise _lib.MvgError("mvg_project_sample_workspace_bytes: bad parameters")
+    work = torch.empty(((nbytes + 3) // 4,), dtype=torch.int32, device=dev)
     check(lib.mvg_project_sample_fused(_lib.ptr(ref3d), _lib.ptr(cams), value_hm.data_ptr(), gmap.data_ptr(),
                                        qproj.data_ptr(), C.byref(prm), sampled.data_ptr(),
                                        ref2d.data_ptr(), bounding.data_ptr(), _lib.ptr(refl),

@@ -27,6 +27,9 @@ from helpers import bf16_round, scene_to
 from oracle import decoder_oracle as orc
 
 
+WELL_CONDITIONED = 0.5      # sigma_4 / sigma_3 of the DLT system below this: the triangulation is well posed
+
+
 def rounded_state_dict(sd):
     """bf16-round exactly the tensors the tensor-core path consumes in bf16."""
     out = {}
@@ -76,9 +79,16 @@ def oracle_chain(sc_r, sdr, L, thr, filter_query=True):
                                                threshold=thr, filter_query=filter_query,
                                                svd_dtype=torch.float64, return_debug=True)
             x32 = orc.triangulate_dlt(dbg["proj_matrices"], dbg["kp_undist"], dbg["conf"], dtype=None)
+            # conditioning of every DLT system: sigma_4 / sigma_3 of the oracle's A.  Towards 1 the two
+            # smallest singular values collide and the EXACT solution itself moves by metres under a
+            # 0.005 px change of the 2D points, so millimetres are meaningless there
+            sv = torch.linalg.svdvals(orc.build_dlt_rows(dbg["proj_matrices"], dbg["kp_undist"], dbg["conf"]).double())
         ref32 = torch.zeros(B, Q, 15, 3)
         ref32[dbg["b_valid"], dbg["q_valid"]] = x32
-        layers.append(dict(tgt_in=tgt, ref_in=ref, out=r, bounding=dbg["bounding"], ref32=ref32.flatten(1, 2)))
+        ratio = torch.ones(B, Q, 15)
+        ratio[dbg["b_valid"], dbg["q_valid"]] = (sv[:, 3] / sv[:, 2]).float().view(-1, 15)
+        layers.append(dict(tgt_in=tgt, ref_in=ref, out=r, bounding=dbg["bounding"], ref32=ref32.flatten(1, 2),
+                           sv_ratio=ratio))
         tgt, ref = r[0], r[1]
     return layers, time.perf_counter() - t0
 
@@ -123,6 +133,12 @@ def _layer_report(o, ours_bounding, lay, thr, B, Q, V, exclude=None) -> Dict:
     rep["mm_fp32_vs_fp64"] = dist_stats(o32, o64, mj)
     rep["mm_ours_vs_fp64_visible"] = dist_stats(ours3, o64, vis)
     rep["mm_fp32_vs_fp64_visible"] = dist_stats(o32, o64, vis)
+    well = mj & (lay["sv_ratio"] < WELL_CONDITIONED)
+    rep["well_conditioned_fraction"] = float(well.sum()) / max(1, int(mj.sum()))
+    rep["mm_ours_vs_fp64_well"] = dist_stats(ours3, o64, well)
+    rep["mm_ours_vs_fp32_well"] = dist_stats(ours3, o32, well)
+    rep["mm_fp32_vs_fp64_well"] = dist_stats(o32, o64, well)
+    rep["mm_ours_vs_fp64_well_visible"] = dist_stats(ours3, o64, well & vis)
     return rep
 
 
@@ -181,7 +197,15 @@ def summarize(rep: Dict) -> Dict:
             ours_vs_fp32_oracle={k: worst(tf, "mm_ours_vs_fp32", k) for k in ("mean", "median", "p95", "max")},
             fp32_vs_fp64_oracle={k: worst(tf, "mm_fp32_vs_fp64", k) for k in ("mean", "median", "p95", "max")},
             ours_vs_fp64_oracle_visible_joints={k: worst(tf, "mm_ours_vs_fp64_visible", k)
-                                                for k in ("mean", "median", "p95", "max")}),
+                                                for k in ("mean", "median", "p95", "max")},
+            well_conditioned=dict(
+                criterion=f"sigma4/sigma3 < {WELL_CONDITIONED} of the oracle's DLT system",
+                fraction_per_layer=[r["well_conditioned_fraction"] for r in tf],
+                ours_vs_fp64_oracle={k: worst(tf, "mm_ours_vs_fp64_well", k) for k in ("mean", "median", "p95", "max")},
+                ours_vs_fp32_oracle={k: worst(tf, "mm_ours_vs_fp32_well", k) for k in ("mean", "median", "p95", "max")},
+                fp32_vs_fp64_oracle={k: worst(tf, "mm_fp32_vs_fp64_well", k) for k in ("mean", "median", "p95", "max")},
+                ours_vs_fp64_oracle_visible_joints={k: worst(tf, "mm_ours_vs_fp64_well_visible", k)
+                                                    for k in ("mean", "median", "p95", "max")})),
         mm_free_running_last_layer=dict(
             ours_vs_fp64_oracle={k: fr[-1]["mm_ours_vs_fp64"][k] for k in ("mean", "median", "p95", "max")},
             ours_vs_fp32_oracle={k: fr[-1]["mm_ours_vs_fp32"][k] for k in ("mean", "median", "p95", "max")},

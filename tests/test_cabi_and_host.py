@@ -26,7 +26,8 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/mvg_b200.h but not exported"
-    assert set(_lib.SIGNATURES) | {"mvg_last_error", "mvg_abi_version", "mvg_launch_count"} == set(syms)
+    assert set(_lib.SIGNATURES) | {"mvg_last_error", "mvg_abi_version", "mvg_launch_count",
+                                   "mvg_project_sample_workspace_bytes"} == set(syms)
     assert _lib.load().mvg_abi_version() == _lib.ABI_VERSION
 
 
