@@ -58,7 +58,13 @@ constexpr int kPcThreads = 256;    // project_bin block
 #endif
 constexpr int kCore = MVG_CORE;    // key cell edge, level-0 texels
 constexpr int kChunk = 128;        // items per chunk (upper bound)
-constexpr int kPWarps = 16;        // sample_params: warps per CTA
+#ifndef MVG_P_WARPS
+#define MVG_P_WARPS 8
+#endif
+#ifndef MVG_P_MINBLK
+#define MVG_P_MINBLK 2
+#endif
+constexpr int kPWarps = MVG_P_WARPS;   // sample_params: warps per CTA
 constexpr int kGWarps = 16;        // gather_tiles: consumer warps per CTA (+ 1 producer warp)
 constexpr int kScanThreads = 1024;
 constexpr int kRecBytes = 128;     // records of one (item, head, level): 2 block columns x 8 points x 8 B
@@ -301,22 +307,29 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const GatherWs ws) {
 }
 
 // ------------------------------------------------------------------ per-sample parameters
+__device__ __forceinline__ __half2 u32_as_half2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t half2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
 template <int LV> struct ParamScratch {
   float proj[LV][kQP];                    // per pyramid level: Linear outputs (offsets | logits)
 };
 
 __device__ __forceinline__ void fma8_f16(float (&acc)[8], const uint4& c, float w) {
-  const __half2* h = reinterpret_cast<const __half2*>(&c);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = __half22float2(h[i]);
-    acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
-    acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
-  }
+  const float2 f0 = __half22float2(u32_as_half2(c.x)), f1 = __half22float2(u32_as_half2(c.y));
+  const float2 f2 = __half22float2(u32_as_half2(c.z)), f3 = __half22float2(u32_as_half2(c.w));
+  acc[0] = fmaf(w, f0.x, acc[0]); acc[1] = fmaf(w, f0.y, acc[1]);
+  acc[2] = fmaf(w, f1.x, acc[2]); acc[3] = fmaf(w, f1.y, acc[3]);
+  acc[4] = fmaf(w, f2.x, acc[4]); acc[5] = fmaf(w, f2.y, acc[5]);
+  acc[6] = fmaf(w, f3.x, acc[6]); acc[7] = fmaf(w, f3.y, acc[7]);
 }
 
+// Everything downstream of the fp16 map G (sampling offsets, softmax, bilinear weights) is not
+// bit-comparable with the reference anyway, so this kernel uses contracted / approximate fp32
+// (fmaf, ex2.approx, reciprocal multiplies): the location math costs a handful of instructions
+// per sample instead of IEEE divisions.  The bit-exact integer path (`bounding`, selection) does
+// not pass through here; mvg_deform_forward keeps the reference's exact arithmetic.
 template <int LV>
-__global__ void __launch_bounds__(kPWarps * 32, 2)
+__global__ void __launch_bounds__(kPWarps * 32, MVG_P_MINBLK)
 sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ qproj, const MvgSampleParams prm,
                      const float* __restrict__ ref2d, const float* __restrict__ refl_in, const GatherWs ws) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
@@ -330,12 +343,17 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
   // phase-B ownership: head m = lane & 7, sample group sub = lane >> 3 (samples r = sub + 4 i)
   const int m = lane & 7, sub = lane >> 3;
   const int nchunks = ws.ctrs[0];
-  float inv_w[LV], inv_h[LV];
+  float fWl[LV], fHl[LV], sxl[LV], syl[LV];
 #pragma unroll
   for (int l = 0; l < LV; ++l) {
-    inv_w[l] = 1.f / static_cast<float>(prm.level_w[l]);
-    inv_h[l] = 1.f / static_cast<float>(prm.level_h[l]);
+    fWl[l] = static_cast<float>(prm.level_w[l]);
+    fHl[l] = static_cast<float>(prm.level_h[l]);
+    sxl[l] = fdiv(fWl[l], fsub(fWl[l], 1.f));        // dq_decoder.py:570-573: r * W / (W - 1)
+    syl[l] = fdiv(fHl[l], fsub(fHl[l], 1.f));
   }
+  // record pointer of (head m, level 0, position 0), this lane's slot pair
+  uint2* const rec_lane = ws.params + static_cast<int64_t>(m) * LV * ws.items * 16 + sub * 2;
+  const int64_t lvl_stride = ws.items * 16;
 #pragma unroll 1
   for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     const int4 ch = ws.chunks[chunk];
@@ -346,59 +364,69 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
     int bbx0[LV], bby0[LV], bbx1[LV], bby1[LV];
 #pragma unroll
     for (int l = 0; l < LV; ++l) { bbx0[l] = bby0[l] = INT_MAX; bbx1[l] = bby1[l] = INT_MIN; }
+    const int bv = ch.z;
+    const int v = bv % V, b = bv / V;
+    const __half* grow = gmap + static_cast<int64_t>(v * B + b) * prm.spatial_size * ldg + lane * 8;
+    const float* qrow = qproj + static_cast<int64_t>(b) * N * kQP + lane * 8;
+    const int item_base = bv * N;
+    // software prefetch of the next item's id + reference point
+    int item = 0;
+    float2 rr = make_float2(0.f, 0.f);
+    if (warp < ch.y) {
+      item = ws.sorted[ch.x + warp];
+      if (refl_in == nullptr) rr = __ldg(reinterpret_cast<const float2*>(ref2d) + item);
+    }
 #pragma unroll 1
     for (int idx = warp; idx < ch.y; idx += kPWarps) {
       const int pos = ch.x + idx;
-      const int64_t item = ws.sorted[pos];
-      const int n = static_cast<int>(item % N);
-      const int bv = static_cast<int>(item / N);
-      const int v = bv % V, b = bv / V;
-      const int64_t vrow0 = static_cast<int64_t>(v * B + b) * prm.spatial_size;     // first row of this view
-      const __half* grow = gmap + vrow0 * ldg;
+      const int cur = item;
+      const int n = cur - item_base;
       float refl_x[LV], refl_y[LV];
       if (refl_in != nullptr) {          // ProjAttn.forward entry: reference points are given
 #pragma unroll
         for (int l = 0; l < LV; ++l) {
-          refl_x[l] = __ldg(refl_in + (item * LV + l) * 2);
-          refl_y[l] = __ldg(refl_in + (item * LV + l) * 2 + 1);
+          refl_x[l] = __ldg(refl_in + (static_cast<int64_t>(cur) * LV + l) * 2);
+          refl_y[l] = __ldg(refl_in + (static_cast<int64_t>(cur) * LV + l) * 2 + 1);
         }
       } else {
-        const float2 r = __ldg(reinterpret_cast<const float2*>(ref2d + 2 * item));
 #pragma unroll
-        for (int l = 0; l < LV; ++l) {   // dq_decoder.py:570-573
-          const float fW = static_cast<float>(prm.level_w[l]), fH = static_cast<float>(prm.level_h[l]);
-          refl_x[l] = fdiv(fmul(r.x, fW), fsub(fW, 1.f));
-          refl_y[l] = fdiv(fmul(r.y, fH), fsub(fH, 1.f));
+        for (int l = 0; l < LV; ++l) {
+          refl_x[l] = rr.x * sxl[l];
+          refl_y[l] = rr.y * syl[l];
         }
+      }
+      if (idx + kPWarps < ch.y) {
+        item = ws.sorted[pos + kPWarps];
+        if (refl_in == nullptr) rr = __ldg(reinterpret_cast<const float2*>(ref2d) + item);
       }
       // ---------------- phase A (a4 i+iii): sample the pre-projected map G at the reference point
       if (lane < kQP / 8) {
-        const float* qp = qproj + (static_cast<int64_t>(b) * N + n) * kQP + lane * 8;
-        const float4 q0 = __ldg(reinterpret_cast<const float4*>(qp));
-        const float4 q1 = __ldg(reinterpret_cast<const float4*>(qp + 4));
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(qrow + n * kQP));
+        const float4 q1 = __ldg(reinterpret_cast<const float4*>(qrow + n * kQP + 4));
         uint4 cn[LV][4];
         float cwgt[LV][4];
 #pragma unroll
         for (int l = 0; l < LV; ++l) {
           const int W = prm.level_w[l], H = prm.level_h[l];
           // F.grid_sample(bilinear, zeros, align_corners=False): projattn.py:139-153
-          const float gx = fminf(fmaxf(fsub(fmul(refl_x[l], 2.f), 1.f), -1.1f), 1.1f);
-          const float gy = fminf(fmaxf(fsub(fmul(refl_y[l], 2.f), 1.f), -1.1f), 1.1f);
-          const float ix = fsub(fmul(fadd(gx, 1.f), fmul(static_cast<float>(W), 0.5f)), 0.5f);
-          const float iy = fsub(fmul(fadd(gy, 1.f), fmul(static_cast<float>(H), 0.5f)), 0.5f);
+          // ix = ((2 r - 1) + 1) * W / 2 - 0.5 = r * W - 0.5 (grid clamped to [-1.1, 1.1])
+          const float gx = fminf(fmaxf(fmaf(refl_x[l], 2.f, -1.f), -1.1f), 1.1f);
+          const float gy = fminf(fmaxf(fmaf(refl_y[l], 2.f, -1.f), -1.1f), 1.1f);
+          const float ix = fmaf(gx + 1.f, fWl[l] * 0.5f, -0.5f);
+          const float iy = fmaf(gy + 1.f, fHl[l] * 0.5f, -0.5f);
           const float fx0 = floorf(ix), fy0 = floorf(iy);
           const int x0 = static_cast<int>(fx0), yy0 = static_cast<int>(fy0);
-          const float we = fsub(ix, fx0), ww = fsub(1.f, we);
-          const float wso = fsub(iy, fy0), wn = fsub(1.f, wso);
+          const float we = ix - fx0, ww = 1.f - we;
+          const float wso = iy - fy0, wn = 1.f - wso;
           const bool okx0 = x0 >= 0 && x0 < W, okx1 = x0 + 1 >= 0 && x0 + 1 < W;
           const bool oky0 = yy0 >= 0 && yy0 < H, oky1 = yy0 + 1 >= 0 && yy0 + 1 < H;
           const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
           const int ya = min(max(yy0, 0), H - 1), yb = min(max(yy0 + 1, 0), H - 1);
-          const __half* gl = grow + static_cast<int64_t>(prm.level_start[l]) * ldg + lane * 8;
-          cn[l][0] = ldg_nc_v4(gl + static_cast<int64_t>(ya * W + xa) * ldg);
-          cn[l][1] = ldg_nc_v4(gl + static_cast<int64_t>(ya * W + xb) * ldg);
-          cn[l][2] = ldg_nc_v4(gl + static_cast<int64_t>(yb * W + xa) * ldg);
-          cn[l][3] = ldg_nc_v4(gl + static_cast<int64_t>(yb * W + xb) * ldg);
+          const __half* gl = grow + static_cast<int64_t>(prm.level_start[l]) * ldg;
+          cn[l][0] = ldg_nc_v4(gl + (ya * W + xa) * ldg);
+          cn[l][1] = ldg_nc_v4(gl + (ya * W + xb) * ldg);
+          cn[l][2] = ldg_nc_v4(gl + (yb * W + xa) * ldg);
+          cn[l][3] = ldg_nc_v4(gl + (yb * W + xb) * ldg);
           cwgt[l][0] = (oky0 && okx0) ? wn * ww : 0.f;
           cwgt[l][1] = (oky0 && okx1) ? wn * we : 0.f;
           cwgt[l][2] = (oky1 && okx0) ? wso * ww : 0.f;
@@ -431,54 +459,59 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < NS / 4; ++i) {
-          lg[i] = expf(lg[i] - mx);
+          lg[i] = __expf(lg[i] - mx);
           sum += lg[i];
         }
         sum += __shfl_xor_sync(0xffffffffu, sum, 8);
         sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-        const float inv_sum = 1.f / sum;
+        const float inv_sum = __fdividef(1.f, sum);
+        uint2* rec_item = rec_lane + static_cast<int64_t>(pos) * 16;
 #pragma unroll
-        for (int i = 0; i < NS / 4; ++i) {
-          const int r = sub + 4 * i;
-          const int l = i >> 1;                        // == r >> 3 because sub < 4 (static index)
-          const float wgt = lg[i] * inv_sum;
-          const int f = m * (NS * 2) + 2 * r;          // flat offset index after the `.view`
-          const float2 off = *reinterpret_cast<const float2*>(&sc.proj[f >> 7][f & 127]);
+        for (int l = 0; l < LV; ++l) {
           const int W = prm.level_w[l], H = prm.level_h[l];
-          const float rlx = refl_x[l], rly = refl_y[l];
-          const float fW = static_cast<float>(W), fH = static_cast<float>(H);
-          // projattn.py:186-191, then deform_im2col_cuda.cuh:291-301 and :41-93
-          // (reciprocal instead of the reference's division: the offsets come from the fp16 map,
-          //  so this path is not bit-comparable anyway; mvg_deform_forward keeps exact inputs)
-          const float loc_x = fadd(rlx, fmul(off.x, inv_w[l]));
-          const float loc_y = fadd(rly, fmul(off.y, inv_h[l]));
-          const float h_im = fsub(fmul(loc_y, fH), 0.5f);
-          const float w_im = fsub(fmul(loc_x, fW), 0.5f);
-          const bool inside = h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW;
-          const float fh = floorf(h_im), fw = floorf(w_im);
+          const float fW = fWl[l], fH = fHl[l];
+          // projattn.py:186-191 (loc = ref + off / (W, H)), then deform_im2col_cuda.cuh:291-301
+          // (im = loc * size - 0.5): im = ref * size + off - 0.5
+          const float bx = fmaf(refl_x[l], fW, -0.5f), by = fmaf(refl_y[l], fH, -0.5f);
           // a sample the reference skips keeps weight 0 and is parked on the reference point's
           // texel, so that it does not stretch the tile box
-          const int h_low = inside ? static_cast<int>(fh) : static_cast<int>(floorf(fminf(fmaxf(fsub(fmul(rly, fH), 0.5f), 0.f), fH)));
-          const int w_low = inside ? static_cast<int>(fw) : static_cast<int>(floorf(fminf(fmaxf(fsub(fmul(rlx, fW), 0.5f), 0.f), fW)));
-          const float lh = inside ? h_im - fh : 0.f, lw = inside ? w_im - fw : 0.f;
-          const float hh = 1.f - lh, hw = 1.f - lw;
-          // The 2x2 texel block is clamped into the level ((ha, wa) .. (ha+1, wa+1) always exist,
-          // H, W >= 2); a corner the reference skips (deform_im2col_cuda.cuh:57-80) gets weight 0
-          // and the surviving row / column moves to the block row / column that holds its texel.
-          const int ha = min(max(h_low, 0), H - 2), wa = min(max(w_low, 0), W - 2);
-          const float ry0 = h_low < 0 ? lh : (h_low > H - 2 ? 0.f : hh);
-          const float ry1 = h_low < 0 ? 0.f : (h_low > H - 2 ? hh : lh);
-          const float rx0 = w_low < 0 ? lw : (w_low > W - 2 ? 0.f : hw);
-          const float rx1 = w_low < 0 ? 0.f : (w_low > W - 2 ? hw : lw);
-          const float sw = inside ? wgt : 0.f;
-          bbx0[l] = min(bbx0[l], wa); bbx1[l] = max(bbx1[l], wa);
-          bby0[l] = min(bby0[l], ha); bby1[l] = max(bby1[l], ha);
-          const uint32_t xy = static_cast<uint32_t>(wa) | (static_cast<uint32_t>(ha) << 16);
-          // slot order inside a block column: points (q, q + 4) adjacent, so that the gather lane of
-          // quarter q reads its two records with one 16-byte load
-          uint2* rec = ws.params + ((static_cast<int64_t>(m) * LV + l) * ws.items + pos) * 16 + sub * 2 + (i & 1);
-          rec[0] = make_uint2(xy, pack_f16x2(ry0 * rx0 * sw, ry1 * rx0 * sw));      // left block column
-          rec[8] = make_uint2(xy, pack_f16x2(ry0 * rx1 * sw, ry1 * rx1 * sw));      // right block column
+          const int park_x = static_cast<int>(fminf(fmaxf(bx, 0.f), fW - 2.f));
+          const int park_y = static_cast<int>(fminf(fmaxf(by, 0.f), fH - 2.f));
+          int lx0 = INT_MAX, ly0 = INT_MAX, lx1 = INT_MIN, ly1 = INT_MIN;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = 2 * l + e;                     // sample r = sub + 4 i of this head
+            const int r = sub + 4 * i;
+            const float wgt = lg[i] * inv_sum;
+            const int f = m * (NS * 2) + 2 * r;          // flat offset index after the `.view`
+            const float2 off = *reinterpret_cast<const float2*>(&sc.proj[f >> 7][f & 127]);
+            const float w_im = bx + off.x, h_im = by + off.y;
+            const bool inside = h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW;
+            const float fh = floorf(h_im), fw = floorf(w_im);
+            const int h_low = static_cast<int>(fh), w_low = static_cast<int>(fw);
+            const float lh = h_im - fh, lw = w_im - fw;
+            const float hh = 1.f - lh, hw = 1.f - lw;
+            // The 2x2 texel block is clamped into the level ((ha, wa) .. (ha+1, wa+1) always exist,
+            // H, W >= 2); a corner the reference skips (deform_im2col_cuda.cuh:57-80) gets weight 0
+            // and the surviving row / column moves to the block row / column that holds its texel.
+            const int ha = inside ? min(max(h_low, 0), H - 2) : park_y;
+            const int wa = inside ? min(max(w_low, 0), W - 2) : park_x;
+            const float sw = inside ? wgt : 0.f;
+            const float ry0 = (h_low < 0 ? lh : (h_low > H - 2 ? 0.f : hh)) * sw;
+            const float ry1 = (h_low < 0 ? 0.f : (h_low > H - 2 ? hh : lh)) * sw;
+            const float rx0 = w_low < 0 ? lw : (w_low > W - 2 ? 0.f : hw);
+            const float rx1 = w_low < 0 ? 0.f : (w_low > W - 2 ? hw : lw);
+            lx0 = min(lx0, wa); lx1 = max(lx1, wa);
+            ly0 = min(ly0, ha); ly1 = max(ly1, ha);
+            const uint32_t xy = static_cast<uint32_t>(wa) | (static_cast<uint32_t>(ha) << 16);
+            // slot order inside a block column: points (q, q + 4) adjacent, so that the gather lane of
+            // quarter q reads its two records with one 16-byte load
+            uint2* rec = rec_item + l * lvl_stride + e;
+            rec[0] = make_uint2(xy, pack_f16x2(ry0 * rx0, ry1 * rx0));      // left block column
+            rec[8] = make_uint2(xy, pack_f16x2(ry0 * rx1, ry1 * rx1));      // right block column
+          }
+          bbx0[l] = min(bbx0[l], lx0); bbx1[l] = max(bbx1[l], lx1);
+          bby0[l] = min(bby0[l], ly0); bby1[l] = max(bby1[l], ly1);
         }
       }
       __syncwarp();   // scratch is reused by the next item
@@ -532,47 +565,39 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // lane holds channel (lane & 3) * 8 + bit4 * 4 + bit3 * 2 + bit2 of the head.
 template <bool kShared>
 __device__ __forceinline__ float gather_two(const uint2 r0, const uint2 r1, uint32_t sbase, const uint4* gbase,
-                                            int bw, int bx0, int by0, int lane) {
-  __half2 acc[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) acc[k] = __float2half2_rn(0.f);
-  const int lc = lane & 7;               // dx * 4 + c: 16-byte unit inside the 128-byte corner pair
+                                            int bw, int lane) {
+  // sbase (shared): region + (lane & 7) * 16 - (box_y0 * bw + box_x0) * 64, so that the address of
+  //   texel (x0, y0) is sbase + (y0 * bw + x0) * 64;  gbase (global): level base + (lane & 7)
+  __half2 a0 = __float2half2_rn(0.f), a1 = a0, a2 = a0, a3 = a0;   // scalars: an array here ends up in local memory
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const uint2 r = s ? r1 : r0;
-    const int x0 = static_cast<int>(r.x & 0xffffu), y0 = static_cast<int>(r.x >> 16);
-    const int t = (y0 - by0) * bw + (x0 - bx0);
+    const uint32_t x0 = r.x & 0xffffu, y0 = r.x >> 16;
     uint4 top, bot;
     if (kShared) {
-      const uint32_t a = sbase + static_cast<uint32_t>(t * 4 + lc) * 16u;
+      const uint32_t a = sbase + (y0 * static_cast<uint32_t>(bw) + x0) * 64u;
       top = lds128(a);
       bot = lds128(a + static_cast<uint32_t>(bw) * 64u);
     } else {
-      const uint4* p = gbase + static_cast<int64_t>(t) * 4 + lc;
+      const uint4* p = gbase + static_cast<int64_t>(y0 * static_cast<uint32_t>(bw) + x0) * 4;
       top = __ldg(p);
       bot = __ldg(p + bw * 4);
     }
-    const __half2 w = *reinterpret_cast<const __half2*>(&r.y);
+    const __half2 w = u32_as_half2(r.y);
     const __half2 wt = __low2half2(w), wb = __high2half2(w);
-    const __half2* th = reinterpret_cast<const __half2*>(&top);
-    const __half2* bh = reinterpret_cast<const __half2*>(&bot);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      acc[k] = __hfma2(wt, th[k], acc[k]);
-      acc[k] = __hfma2(wb, bh[k], acc[k]);
-    }
+    a0 = __hfma2(wt, u32_as_half2(top.x), a0); a0 = __hfma2(wb, u32_as_half2(bot.x), a0);
+    a1 = __hfma2(wt, u32_as_half2(top.y), a1); a1 = __hfma2(wb, u32_as_half2(bot.y), a1);
+    a2 = __hfma2(wt, u32_as_half2(top.z), a2); a2 = __hfma2(wb, u32_as_half2(bot.z), a2);
+    a3 = __hfma2(wt, u32_as_half2(top.w), a3); a3 = __hfma2(wb, u32_as_half2(bot.w), a3);
   }
-  auto xchg = [](const __half2 v, int o) {
-    const uint32_t u = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<const uint32_t*>(&v), o);
-    return *reinterpret_cast<const __half2*>(&u);
-  };
   const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-  __half2 k0 = b4 ? acc[2] : acc[0], k1 = b4 ? acc[3] : acc[1];
-  k0 = __hadd2(k0, xchg(b4 ? acc[0] : acc[2], 16));
-  k1 = __hadd2(k1, xchg(b4 ? acc[1] : acc[3], 16));
-  __half2 kk = b3 ? k1 : k0;
-  kk = __hadd2(kk, xchg(b3 ? k0 : k1, 8));
-  kk = __hadd2(kk, xchg(kk, 4));
+  const uint32_t u0 = half2_as_u32(a0), u1 = half2_as_u32(a1), u2 = half2_as_u32(a2), u3 = half2_as_u32(a3);
+  const uint32_t keep0 = b4 ? u2 : u0, keep1 = b4 ? u3 : u1, send0 = b4 ? u0 : u2, send1 = b4 ? u1 : u3;
+  const __half2 k0 = __hadd2(u32_as_half2(keep0), u32_as_half2(__shfl_xor_sync(0xffffffffu, send0, 16)));
+  const __half2 k1 = __hadd2(u32_as_half2(keep1), u32_as_half2(__shfl_xor_sync(0xffffffffu, send1, 16)));
+  const uint32_t v0 = half2_as_u32(k0), v1 = half2_as_u32(k1);
+  __half2 kk = __hadd2(u32_as_half2(b3 ? v1 : v0), u32_as_half2(__shfl_xor_sync(0xffffffffu, b3 ? v0 : v1, 8)));
+  kk = __hadd2(kk, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(kk), 4)));
   return b2 ? __high2float(kk) : __low2float(kk);
 }
 __device__ __forceinline__ int lane_channel(int lane) {
@@ -706,18 +731,28 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
       for (int l = 0; l < LV; ++l) {
         if (l > 0) mbar_wait(&full[l], par);
         const int4 box = d->box[l];
+        const uint32_t tile = region[l] + static_cast<uint32_t>(lane & 7) * 16u -
+                              static_cast<uint32_t>(box.y * box.z + box.x) * 64u;
+        const uint32_t rcs = recs[l] + rec_lane;
+        // two items per iteration: their load -> blend -> shuffle chains are independent and overlap
 #pragma unroll 1
-        for (int i = warp, k = 0; i < count; i += kGWarps, ++k) {
-          const uint4 rc = lds128(recs[l] + static_cast<uint32_t>(i) * kRecBytes + rec_lane);
-          const float vsum = gather_two<true>(make_uint2(rc.x, rc.y), make_uint2(rc.z, rc.w), region[l], nullptr,
-                                              box.z, box.x, box.y, lane);
-          float* ps = partial + i * 32 + chn;
-          float tot = vsum;
-          if (l > 0) tot = *ps + vsum;
-          if (l + 1 < LV) *ps = tot;
+        for (int i = warp, k = 0; i < count; i += 2 * kGWarps, k += 2) {
+          const int i2 = i + kGWarps;
+          const bool has2 = i2 < count;
+          const uint4 ra = lds128(rcs + static_cast<uint32_t>(i) * kRecBytes);
+          const uint4 rb = lds128(rcs + static_cast<uint32_t>(has2 ? i2 : i) * kRecBytes);
+          const float va = gather_two<true>(make_uint2(ra.x, ra.y), make_uint2(ra.z, ra.w), tile, nullptr, box.z, lane);
+          const float vb = gather_two<true>(make_uint2(rb.x, rb.y), make_uint2(rb.z, rb.w), tile, nullptr, box.z, lane);
+          float* pa = partial + i * 32 + chn;
+          float* pb = partial + i2 * 32 + chn;
+          float ta = va, tb = vb;
+          if (l > 0) { ta += *pa; if (has2) tb += *pb; }
+          if (l + 1 < LV) { *pa = ta; if (has2) *pb = tb; }
           if (l + 1 == LV) {
-            const int64_t item = __shfl_sync(0xffffffffu, my_item, k);
-            sampled[item * 256 + head * 32 + chn] = __float2bfloat16(tot);
+            const int64_t item_a = __shfl_sync(0xffffffffu, my_item, k);
+            const int64_t item_b = __shfl_sync(0xffffffffu, my_item, k + 1);
+            sampled[item_a * 256 + head * 32 + chn] = __float2bfloat16(ta);
+            if (has2) sampled[item_b * 256 + head * 32 + chn] = __float2bfloat16(tb);
           }
         }
         __syncwarp();
@@ -757,8 +792,8 @@ gather_direct_kernel(const __half* __restrict__ value_hm, const MvgSampleParams 
     for (int l = 0; l < LV; ++l) {
       const uint4 rc = __ldg(reinterpret_cast<const uint4*>(rec + l * ws.items * 16));
       const uint2 c0 = make_uint2(rc.x, rc.y), c1 = make_uint2(rc.z, rc.w);
-      const uint4* gb = reinterpret_cast<const uint4*>(vh + (vrow0 + prm.level_start[l]) * 32);
-      const float vsum = gather_two<false>(c0, c1, 0u, gb, prm.level_w[l], 0, 0, lane);
+      const uint4* gb = reinterpret_cast<const uint4*>(vh + (vrow0 + prm.level_start[l]) * 32) + (lane & 7);
+      const float vsum = gather_two<false>(c0, c1, 0u, gb, prm.level_w[l], lane);
       tot = l == 0 ? vsum : tot + vsum;
     }
     const int64_t item = ws.sorted[ch.x + i];
@@ -791,7 +826,7 @@ static int launch_gather(const __half* vhm, const __half* gmp, const float* qpro
     pattr_done = true;
   }
   const int64_t chunks_bound = ws.items / kChunk + ws.keys + 1;
-  const int pgrid = static_cast<int>(chunks_bound < 2 * kNumSMs ? chunks_bound : 2 * kNumSMs);
+  const int pgrid = static_cast<int>(chunks_bound < MVG_P_MINBLK * kNumSMs ? chunks_bound : MVG_P_MINBLK * kNumSMs);
   sample_params_kernel<LV><<<pgrid, kPWarps * 32, psmem, st>>>(gmp, qproj, prm, ref2d, refl_in, ws);
   int rc = check_launch("mvg_project_sample_fused(sample_params)");
   if (rc != MVG_OK) return rc;
