@@ -161,8 +161,8 @@ MVG_API int mvg_value_proj_gemm(const void* feat, const void* W, const float* bi
  *   (dq_decoder.py:585-586) and reads it nowhere else, so they are not gathered; their
  *   `sampled` rows are zeros.
  * Arithmetic: geometry, softmax and the bilinear x attention weights in fp32; the weights are then
- *   rounded to fp16 and the blend of a pyramid level runs in packed fp16 (HFMA2), levels are summed
- *   in fp32.  Items are binned by image cell and gathered from shared-memory tiles staged by
+ *   rounded to fp16 and the 96-term blend of an (item, head) runs in packed fp16 (HFMA2; the bf16
+ *   rounding of `sampled` is coarser than its accumulation error).  Items are binned by image cell and gathered from shared-memory tiles staged by
  *   cp.async.bulk (csrc/project_sample.cu).
  * `workspace`: device, 256-byte aligned, mvg_project_sample_workspace_bytes(prm) bytes, contents
  *   irrelevant on entry; its first B*V int32 receive the in-view item count of every (frame, view).

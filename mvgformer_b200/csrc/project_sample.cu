@@ -54,7 +54,7 @@ constexpr int kQP = 192;           // 128 offset channels + 64 logit channels pe
 constexpr int kHeads = 8;
 constexpr int kPcThreads = 256;    // project_bin block
 #ifndef MVG_CORE
-#define MVG_CORE 16
+#define MVG_CORE 20
 #endif
 constexpr int kCore = MVG_CORE;    // key cell edge, level-0 texels
 constexpr int kChunk = 128;        // items per chunk (upper bound)
@@ -67,22 +67,24 @@ constexpr int kChunk = 128;        // items per chunk (upper bound)
 constexpr int kPWarps = MVG_P_WARPS;   // sample_params: warps per CTA
 constexpr int kGWarps = 16;        // gather_tiles: consumer warps per CTA (+ 1 producer warp)
 constexpr int kScanThreads = 1024;
+constexpr int kIPW = kChunk / kGWarps;   // items per consumer warp and unit
 constexpr int kRecBytes = 128;     // records of one (item, head, level): 2 block columns x 8 points x 8 B
 
 // per-level shared-memory region capacity in texels (64 B each) for the tiled gather
-// (227 KB - LV x 16 KB record regions - 16 KB partial sums)
+// (227 KB - LV x 16 KB record regions)
 template <int LV>
 __host__ __device__ constexpr int region_cap(int l) {
-  return LV == 1 ? (l == 0 ? 3072 : 0)
-       : LV == 2 ? (l == 0 ? 1856 : l == 1 ? 960 : 0)
-       : LV == 3 ? (l == 0 ? 1408 : l == 1 ? 704 : l == 2 ? 480 : 0)
-                 : (l == 0 ? 1152 : l == 1 ? 608 : l == 2 ? 384 : l == 3 ? 192 : 0);
+  return LV == 1 ? (l == 0 ? 3328 : 0)
+       : LV == 2 ? (l == 0 ? 2048 : l == 1 ? 1024 : 0)
+       : LV == 3 ? (l == 0 ? 1536 : l == 1 ? 768 : l == 2 ? 544 : 0)
+                 : (l == 0 ? 1280 : l == 1 ? 672 : l == 2 ? 416 : l == 3 ? 224 : 0);
 }
 
 struct GatherWs {
   int* counts;        // [BV]            in-view items per (frame, view)       (zeroed per call)
   int* hist;          // [keys]          items per key                          (zeroed per call)
-  int* ctrs;          // [8]             0 chunks, 1 in-view items, 2 unit cursor, 3 direct units (zeroed)
+  int* ctrs;          // [8]             0 chunks, 1 in-view items, 2 unit cursor, 3 direct units,
+                      //                 5 chunk cursor of sample_params (zeroed)
   int* key_off;       // [keys]
   int* key_chunk0;    // [keys + 1]
   int* item_key;      // [items]
@@ -290,7 +292,6 @@ bin_scan_kernel(const GatherWs ws, int cells_per_bv) {
       const int mid = (lo + hi) >> 1;
       if (ws.key_chunk0[mid] <= c) lo = mid; else hi = mid;
     }
-    // skip empty keys that share the same first chunk: take the LAST key with key_chunk0 <= c
     const int j = c - ws.key_chunk0[lo];
     const int cnt = ws.hist[lo];
     const int nch = (cnt + kChunk - 1) / kChunk;
@@ -354,10 +355,15 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
   // record pointer of (head m, level 0, position 0), this lane's slot pair
   uint2* const rec_lane = ws.params + static_cast<int64_t>(m) * LV * ws.items * 16 + sub * 2;
   const int64_t lvl_stride = ws.items * 16;
+  __shared__ int s_chunk;
 #pragma unroll 1
-  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+  for (;;) {
+    __syncthreads();                     // previous chunk's boxes were written out, s_chunk was read
+    if (threadIdx.x == 0) s_chunk = atomicAdd(ws.ctrs + 5, 1);      // work queue: chunks differ in size
+    __syncthreads();
+    const int chunk = s_chunk;
+    if (chunk >= nchunks) break;
     const int4 ch = ws.chunks[chunk];
-    __syncthreads();                     // previous chunk's boxes were written out
     for (int i = threadIdx.x; i < kHeads * LV * 4; i += blockDim.x)
       (&s_bb[0][0][0])[i] = (i & 2) ? INT_MIN : INT_MAX;
     __syncthreads();
@@ -370,6 +376,8 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
     const float* qrow = qproj + static_cast<int64_t>(b) * N * kQP + lane * 8;
     const int item_base = bv * N;
     // software prefetch of the next item's id + reference point
+    // (measured and dropped: a cross-item pipeline that keeps item i+1's 12 corner rows in flight during
+    //  item i's phase B - 168 registers, 12 warps per SM, 145 us vs 127 us for this version)
     int item = 0;
     float2 rr = make_float2(0.f, 0.f);
     if (warp < ch.y) {
@@ -403,10 +411,10 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
       if (lane < kQP / 8) {
         const float4 q0 = __ldg(reinterpret_cast<const float4*>(qrow + n * kQP));
         const float4 q1 = __ldg(reinterpret_cast<const float4*>(qrow + n * kQP + 4));
-        uint4 cn[LV][4];
-        float cwgt[LV][4];
-#pragma unroll
-        for (int l = 0; l < LV; ++l) {
+        // one level in flight ahead of the one being blended: 8 corner rows live instead of 12
+        uint4 cn[2][4];
+        float cwgt[2][4];
+        auto issue = [&](int l, uint4 (&c)[4], float (&w)[4]) {
           const int W = prm.level_w[l], H = prm.level_h[l];
           // F.grid_sample(bilinear, zeros, align_corners=False): projattn.py:139-153
           // ix = ((2 r - 1) + 1) * W / 2 - 0.5 = r * W - 0.5 (grid clamped to [-1.1, 1.1])
@@ -423,20 +431,22 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
           const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
           const int ya = min(max(yy0, 0), H - 1), yb = min(max(yy0 + 1, 0), H - 1);
           const __half* gl = grow + static_cast<int64_t>(prm.level_start[l]) * ldg;
-          cn[l][0] = ldg_nc_v4(gl + (ya * W + xa) * ldg);
-          cn[l][1] = ldg_nc_v4(gl + (ya * W + xb) * ldg);
-          cn[l][2] = ldg_nc_v4(gl + (yb * W + xa) * ldg);
-          cn[l][3] = ldg_nc_v4(gl + (yb * W + xb) * ldg);
-          cwgt[l][0] = (oky0 && okx0) ? wn * ww : 0.f;
-          cwgt[l][1] = (oky0 && okx1) ? wn * we : 0.f;
-          cwgt[l][2] = (oky1 && okx0) ? wso * ww : 0.f;
-          cwgt[l][3] = (oky1 && okx1) ? wso * we : 0.f;
-        }
+          c[0] = ldg_nc_v4(gl + (ya * W + xa) * ldg);
+          c[1] = ldg_nc_v4(gl + (ya * W + xb) * ldg);
+          c[2] = ldg_nc_v4(gl + (yb * W + xa) * ldg);
+          c[3] = ldg_nc_v4(gl + (yb * W + xb) * ldg);
+          w[0] = (oky0 && okx0) ? wn * ww : 0.f;
+          w[1] = (oky0 && okx1) ? wn * we : 0.f;
+          w[2] = (oky1 && okx0) ? wso * ww : 0.f;
+          w[3] = (oky1 && okx1) ? wso * we : 0.f;
+        };
+        issue(0, cn[0], cwgt[0]);
 #pragma unroll
         for (int l = 0; l < LV; ++l) {
+          if (l + 1 < LV) issue(l + 1, cn[(l + 1) & 1], cwgt[(l + 1) & 1]);
           float r8[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) fma8_f16(r8, cn[l][c], cwgt[l][c]);
+          for (int c = 0; c < 4; ++c) fma8_f16(r8, cn[l & 1][c], cwgt[l & 1][c]);
           float4* dst = reinterpret_cast<float4*>(&sc.proj[l][lane * 8]);
           dst[0] = make_float4(r8[0], r8[1], r8[2], r8[3]);
           dst[1] = make_float4(r8[4], r8[5], r8[6], r8[7]);
@@ -478,6 +488,7 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
           const int park_x = static_cast<int>(fminf(fmaxf(bx, 0.f), fW - 2.f));
           const int park_y = static_cast<int>(fminf(fmaxf(by, 0.f), fH - 2.f));
           int lx0 = INT_MAX, ly0 = INT_MAX, lx1 = INT_MIN, ly1 = INT_MIN;
+          uint32_t rxy[2], rw0[2], rw1[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int i = 2 * l + e;                     // sample r = sub + 4 i of this head
@@ -503,13 +514,16 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
             const float rx1 = w_low < 0 ? 0.f : (w_low > W - 2 ? hw : lw);
             lx0 = min(lx0, wa); lx1 = max(lx1, wa);
             ly0 = min(ly0, ha); ly1 = max(ly1, ha);
-            const uint32_t xy = static_cast<uint32_t>(wa) | (static_cast<uint32_t>(ha) << 16);
-            // slot order inside a block column: points (q, q + 4) adjacent, so that the gather lane of
-            // quarter q reads its two records with one 16-byte load
-            uint2* rec = rec_item + l * lvl_stride + e;
-            rec[0] = make_uint2(xy, pack_f16x2(ry0 * rx0, ry1 * rx0));      // left block column
-            rec[8] = make_uint2(xy, pack_f16x2(ry0 * rx1, ry1 * rx1));      // right block column
+            rxy[e] = static_cast<uint32_t>(wa) | (static_cast<uint32_t>(ha) << 16);
+            rw0[e] = pack_f16x2(ry0 * rx0, ry1 * rx0);      // left block column: (top, bottom)
+            rw1[e] = pack_f16x2(ry0 * rx1, ry1 * rx1);      // right block column
           }
+          // slot order inside a block column: points (q, q + 4) adjacent, so that this lane writes - and the
+          // gather lane of quarter q reads - both records with one 16-byte access (whole 32-byte sectors
+          // per head: the 8-byte scattered stores of the first version cost a third of the kernel)
+          uint4* rec = reinterpret_cast<uint4*>(rec_item + l * lvl_stride);
+          rec[0] = make_uint4(rxy[0], rw0[0], rxy[1], rw0[1]);
+          rec[4] = make_uint4(rxy[0], rw1[0], rxy[1], rw1[1]);
           bbx0[l] = min(bbx0[l], lx0); bbx1[l] = max(bbx1[l], lx1);
           bby0[l] = min(bby0[l], ly0); bby1[l] = max(bby1[l], ly1);
         }
@@ -561,18 +575,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 // Two samples of one (item, head, level): lane = quarter q * 8 + block column dx * 4 + 16-byte chunk c
 // gathers, for sample points q and q + 4, the top and bottom texel rows of its block column and blends
-// them in packed fp16; the 8 (q, dx) roles are then summed with a transposing butterfly, after which
-// lane holds channel (lane & 3) * 8 + bit4 * 4 + bit3 * 2 + bit2 of the head.
+// them in packed fp16 into the lane's 8-channel accumulator (a0..a3).  All pyramid levels of an
+// (item, head) accumulate into the same registers.
+//   sbase (shared): region + (lane & 7) * 16 - (box_y0 * bw + box_x0) * 64, so that the address of texel
+//   (x0, y0) is sbase + (y0 * bw + x0) * 64;  gbase (global): level base + (lane & 7).
 template <bool kShared>
-__device__ __forceinline__ float gather_two(const uint2 r0, const uint2 r1, uint32_t sbase, const uint4* gbase,
-                                            int bw, int lane) {
-  // sbase (shared): region + (lane & 7) * 16 - (box_y0 * bw + box_x0) * 64, so that the address of
-  //   texel (x0, y0) is sbase + (y0 * bw + x0) * 64;  gbase (global): level base + (lane & 7)
-  __half2 a0 = __float2half2_rn(0.f), a1 = a0, a2 = a0, a3 = a0;   // scalars: an array here ends up in local memory
+__device__ __forceinline__ void blend_two(const uint4 rc, uint32_t sbase, const uint4* gbase, int bw,
+                                          __half2& a0, __half2& a1, __half2& a2, __half2& a3) {
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    const uint2 r = s ? r1 : r0;
-    const uint32_t x0 = r.x & 0xffffu, y0 = r.x >> 16;
+    const uint32_t rxy = s ? rc.z : rc.x, rw = s ? rc.w : rc.y;
+    const uint32_t x0 = rxy & 0xffffu, y0 = rxy >> 16;
     uint4 top, bot;
     if (kShared) {
       const uint32_t a = sbase + (y0 * static_cast<uint32_t>(bw) + x0) * 64u;
@@ -583,13 +596,42 @@ __device__ __forceinline__ float gather_two(const uint2 r0, const uint2 r1, uint
       top = __ldg(p);
       bot = __ldg(p + bw * 4);
     }
-    const __half2 w = u32_as_half2(r.y);
+    const __half2 w = u32_as_half2(rw);
     const __half2 wt = __low2half2(w), wb = __high2half2(w);
     a0 = __hfma2(wt, u32_as_half2(top.x), a0); a0 = __hfma2(wb, u32_as_half2(bot.x), a0);
     a1 = __hfma2(wt, u32_as_half2(top.y), a1); a1 = __hfma2(wb, u32_as_half2(bot.y), a1);
     a2 = __hfma2(wt, u32_as_half2(top.z), a2); a2 = __hfma2(wb, u32_as_half2(bot.z), a2);
     a3 = __hfma2(wt, u32_as_half2(top.w), a3); a3 = __hfma2(wb, u32_as_half2(bot.w), a3);
   }
+}
+// Two items at once from shared memory (same arithmetic per item as blend_two).
+__device__ __forceinline__ void blend_pair(const uint4 ra, const uint4 rb, uint32_t sbase, int bw,
+                                           __half2 (&a)[4], __half2 (&b)[4]) {
+  const uint32_t bw64 = static_cast<uint32_t>(bw) * 64u;
+  const uint32_t xa0 = ra.x & 0xffffu, ya0 = ra.x >> 16, xa1 = ra.z & 0xffffu, ya1 = ra.z >> 16;
+  const uint32_t xb0 = rb.x & 0xffffu, yb0 = rb.x >> 16, xb1 = rb.z & 0xffffu, yb1 = rb.z >> 16;
+  const uint32_t pa0 = sbase + (ya0 * static_cast<uint32_t>(bw) + xa0) * 64u;
+  const uint32_t pa1 = sbase + (ya1 * static_cast<uint32_t>(bw) + xa1) * 64u;
+  const uint32_t pb0 = sbase + (yb0 * static_cast<uint32_t>(bw) + xb0) * 64u;
+  const uint32_t pb1 = sbase + (yb1 * static_cast<uint32_t>(bw) + xb1) * 64u;
+  const uint4 ta0 = lds128(pa0), ba0 = lds128(pa0 + bw64), ta1 = lds128(pa1), ba1 = lds128(pa1 + bw64);
+  const uint4 tb0 = lds128(pb0), bb0 = lds128(pb0 + bw64), tb1 = lds128(pb1), bb1 = lds128(pb1 + bw64);
+  auto blend = [](const uint4& top, const uint4& bot, uint32_t rw, __half2 (&c)[4]) {
+    const __half2 w = u32_as_half2(rw);
+    const __half2 wt = __low2half2(w), wb = __high2half2(w);
+    c[0] = __hfma2(wt, u32_as_half2(top.x), c[0]); c[0] = __hfma2(wb, u32_as_half2(bot.x), c[0]);
+    c[1] = __hfma2(wt, u32_as_half2(top.y), c[1]); c[1] = __hfma2(wb, u32_as_half2(bot.y), c[1]);
+    c[2] = __hfma2(wt, u32_as_half2(top.z), c[2]); c[2] = __hfma2(wb, u32_as_half2(bot.z), c[2]);
+    c[3] = __hfma2(wt, u32_as_half2(top.w), c[3]); c[3] = __hfma2(wb, u32_as_half2(bot.w), c[3]);
+  };
+  blend(ta0, ba0, ra.y, a);
+  blend(ta1, ba1, ra.w, a);
+  blend(tb0, bb0, rb.y, b);
+  blend(tb1, bb1, rb.w, b);
+}
+// Sums the 8 (q, dx) roles with a transposing butterfly; afterwards lane holds channel
+// (lane & 3) * 8 + bit4 * 4 + bit3 * 2 + bit2 of the head.
+__device__ __forceinline__ float reduce_roles(__half2 a0, __half2 a1, __half2 a2, __half2 a3, int lane) {
   const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
   const uint32_t u0 = half2_as_u32(a0), u1 = half2_as_u32(a1), u2 = half2_as_u32(a2), u3 = half2_as_u32(a3);
   const uint32_t keep0 = b4 ? u2 : u0, keep1 = b4 ? u3 : u1, send0 = b4 ? u0 : u2, send1 = b4 ? u1 : u3;
@@ -613,8 +655,7 @@ template <int LV>
 struct TileSmem {
   static constexpr int kTexels = region_cap<LV>(0) + region_cap<LV>(1) + region_cap<LV>(2) + region_cap<LV>(3);
   static constexpr int kRecOff = kTexels * 64;                       // LV record regions of kChunk x 128 B
-  static constexpr int kPartialOff = kRecOff + LV * kChunk * kRecBytes;
-  static constexpr int kDescOff = kPartialOff + kChunk * 32 * 4;
+  static constexpr int kDescOff = kRecOff + LV * kChunk * kRecBytes;
   static constexpr int kBytes = kDescOff + 2 * static_cast<int>(sizeof(UnitDesc)) + 128;
 };
 
@@ -623,7 +664,6 @@ __global__ void __launch_bounds__((kGWarps + 1) * 32, 1)
 gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams prm,
                     __nv_bfloat16* __restrict__ sampled, const GatherWs ws) {
   extern __shared__ __align__(128) uint8_t smem[];
-  float* partial = reinterpret_cast<float*>(smem + TileSmem<LV>::kPartialOff);       // [kChunk][32]
   UnitDesc* sdesc = reinterpret_cast<UnitDesc*>(smem + TileSmem<LV>::kDescOff);      // [2]
   uint64_t* full = reinterpret_cast<uint64_t*>(sdesc + 2);                           // [LV]
   uint64_t* empty = full + MVG_MAX_LEVELS;                                           // [LV]
@@ -644,13 +684,15 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const int n_units = ws.ctrs[0] * kHeads;
   const int V = prm.views, B = prm.batch;
 
   if (warp == kGWarps) {
     // ===================== producer: unit descriptors, tile rows, record blocks =====================
     // The next unit's metadata (work-queue ticket, chunk, boxes) is fetched right after this unit's
     // level-0 copies are issued, so its global-memory latency hides behind the copies in flight.
+    // (Sharing one set of tiles between the chunks of a dense key was measured and dropped: the
+    //  union boxes grow and a 4-chunk work item unbalances the tail - 189 -> 209 us.)
+    const int n_units = ws.ctrs[0] * kHeads;
     int unit = -1;
     int4 ch = make_int4(0, 0, 0, 0), box[LV];
     auto fetch = [&]() {
@@ -698,13 +740,18 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
         const int bw = cbox[l].z, bh = cbox[l].w;
         const uint32_t row_bytes = static_cast<uint32_t>(bw) * 64u;
         const uint32_t rec_bytes = static_cast<uint32_t>(count) * kRecBytes;
+#ifdef MVG_DEBUG_NOSTAGE      // timing experiment only (wrong results): tiles are staged for the first unit only
+        const int bh_eff = seq == 0 ? bh : 0;
+#else
+        const int bh_eff = bh;
+#endif
         if (lane == 0) {
-          mbar_expect_tx(&full[l], row_bytes * static_cast<uint32_t>(bh) + rec_bytes);
+          mbar_expect_tx(&full[l], row_bytes * static_cast<uint32_t>(bh_eff) + rec_bytes);
           bulk_g2s(recs[l], rec_src + static_cast<int64_t>(l) * ws.items * 16, rec_bytes, &full[l]);
         }
         __syncwarp();
         const __half* src0 = vh + (vrow0 + prm.level_start[l] + static_cast<int64_t>(cbox[l].y) * prm.level_w[l] + cbox[l].x) * 32;
-        for (int r = lane; r < bh; r += 32)
+        for (int r = lane; r < bh_eff; r += 32)
           bulk_g2s(region[l] + static_cast<uint32_t>(r) * row_bytes, src0 + static_cast<int64_t>(r) * prm.level_w[l] * 32,
                    row_bytes, &full[l]);
         if (l == 0) fetch();               // overwrites unit / ch / box: cbox, first, count, head are this unit's
@@ -727,36 +774,42 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
       // ids of the items this warp owns (i = warp + 16 k): lane k keeps item k's id for the final store
       int my_item = 0;
       if (warp + kGWarps * lane < count) my_item = __ldg(ws.sorted + first + warp + kGWarps * lane);
+      // per-lane fp16 accumulators of the warp's <= 8 items, carried across the pyramid levels
+      // (statically unrolled: the independent load -> blend chains of different items overlap)
+      __half2 acc[kIPW][4];
+#pragma unroll
+      for (int k = 0; k < kIPW; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = __float2half2_rn(0.f);
 #pragma unroll
       for (int l = 0; l < LV; ++l) {
         if (l > 0) mbar_wait(&full[l], par);
         const int4 box = d->box[l];
         const uint32_t tile = region[l] + static_cast<uint32_t>(lane & 7) * 16u -
                               static_cast<uint32_t>(box.y * box.z + box.x) * 64u;
-        const uint32_t rcs = recs[l] + rec_lane;
-        // two items per iteration: their load -> blend -> shuffle chains are independent and overlap
-#pragma unroll 1
-        for (int i = warp, k = 0; i < count; i += 2 * kGWarps, k += 2) {
-          const int i2 = i + kGWarps;
-          const bool has2 = i2 < count;
-          const uint4 ra = lds128(rcs + static_cast<uint32_t>(i) * kRecBytes);
-          const uint4 rb = lds128(rcs + static_cast<uint32_t>(has2 ? i2 : i) * kRecBytes);
-          const float va = gather_two<true>(make_uint2(ra.x, ra.y), make_uint2(ra.z, ra.w), tile, nullptr, box.z, lane);
-          const float vb = gather_two<true>(make_uint2(rb.x, rb.y), make_uint2(rb.z, rb.w), tile, nullptr, box.z, lane);
-          float* pa = partial + i * 32 + chn;
-          float* pb = partial + i2 * 32 + chn;
-          float ta = va, tb = vb;
-          if (l > 0) { ta += *pa; if (has2) tb += *pb; }
-          if (l + 1 < LV) { *pa = ta; if (has2) *pb = tb; }
-          if (l + 1 == LV) {
-            const int64_t item_a = __shfl_sync(0xffffffffu, my_item, k);
-            const int64_t item_b = __shfl_sync(0xffffffffu, my_item, k + 1);
-            sampled[item_a * 256 + head * 32 + chn] = __float2bfloat16(ta);
-            if (has2) sampled[item_b * 256 + head * 32 + chn] = __float2bfloat16(tb);
+        const uint32_t rcs = recs[l] + rec_lane + static_cast<uint32_t>(warp) * kRecBytes;
+        // items in pairs: inside a pair both record loads, then all eight tile loads are issued before
+        // the blends, so the shared-memory latency of one item hides behind the other's arithmetic
+#pragma unroll
+        for (int k = 0; k < kIPW; k += 2) {
+          const int ia = warp + kGWarps * k;
+          if (ia + kGWarps < count) {                  // warp-uniform: both items exist
+            const uint4 ra = lds128(rcs + static_cast<uint32_t>(k * kGWarps) * kRecBytes);
+            const uint4 rb = lds128(rcs + static_cast<uint32_t>((k + 1) * kGWarps) * kRecBytes);
+            blend_pair(ra, rb, tile, box.z, acc[k], acc[k + 1]);
+          } else if (ia < count) {
+            const uint4 rc = lds128(rcs + static_cast<uint32_t>(k * kGWarps) * kRecBytes);
+            blend_two<true>(rc, tile, nullptr, box.z, acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[l]);
+      }
+#pragma unroll
+      for (int k = 0; k < kIPW; ++k) {
+        if (warp + kGWarps * k < count) {
+          const float v = reduce_roles(acc[k][0], acc[k][1], acc[k][2], acc[k][3], lane);
+          const int64_t item = __shfl_sync(0xffffffffu, my_item, k);
+          sampled[item * 256 + head * 32 + chn] = __float2bfloat16(v);
+        }
       }
       ++seq;
     }
@@ -787,15 +840,14 @@ gather_direct_kernel(const __half* __restrict__ value_hm, const MvgSampleParams 
     const int64_t vrow0 = static_cast<int64_t>(v * B + b) * prm.spatial_size;
     const __half* vh = value_hm + static_cast<int64_t>(head) * prm.value_head_stride;
     const uint2* rec = ws.params + (static_cast<int64_t>(head) * LV * ws.items + ch.x + i) * 16 + dx * 8 + q * 2;
-    float tot = 0.f;
+    __half2 a0 = __float2half2_rn(0.f), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll
     for (int l = 0; l < LV; ++l) {
       const uint4 rc = __ldg(reinterpret_cast<const uint4*>(rec + l * ws.items * 16));
-      const uint2 c0 = make_uint2(rc.x, rc.y), c1 = make_uint2(rc.z, rc.w);
       const uint4* gb = reinterpret_cast<const uint4*>(vh + (vrow0 + prm.level_start[l]) * 32) + (lane & 7);
-      const float vsum = gather_two<false>(c0, c1, 0u, gb, prm.level_w[l], lane);
-      tot = l == 0 ? vsum : tot + vsum;
+      blend_two<false>(rc, 0u, gb, prm.level_w[l], a0, a1, a2, a3);
     }
+    const float tot = reduce_roles(a0, a1, a2, a3, lane);
     const int64_t item = ws.sorted[ch.x + i];
     sampled[item * 256 + head * 32 + chn] = __float2bfloat16(tot);
   }
