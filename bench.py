@@ -282,6 +282,18 @@ def run_ours(a):
         barrier()
         return float(ms.item())
 
+    def t_ms(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        for _ in range(n):
+            fn()
+        e_.record()
+        torch.cuda.synchronize()
+        return s_.elapsed_time(e_) / n
+
     # ---- device-resident throughput
     for _ in range(max(a.warmup, 3)):
         forward_resident()
@@ -472,18 +484,6 @@ def run_ours(a):
         poses, prob = forward_resident()
         poses, prob = poses.clone(), prob.clone()
 
-        def t_ms(fn, n=20):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s_.record()
-            for _ in range(n):
-                fn()
-            e_.record()
-            torch.cuda.synchronize()
-            return s_.elapsed_time(e_) / n
-
         def run_post():
             pred, vid, vcnt = post.assemble_predictions(poses, prob, a.threshold, J)
             return post.nearby_joints_nms(pred, vid, vcnt, 0.3, 7)
@@ -493,6 +493,34 @@ def run_ours(a):
                     "poses_kept_by_nms_frame0": kept,
                     "note": "device time of mvg_init_queries and mvg_assemble_predictions + "
                             "mvg_nearby_joints_nms on the step's outputs; not part of `value`"}
+
+    # ---- the kernel to beat: the reference's own CUDA op (deform_im2col_cuda.cuh:247-309) compiled for
+    # sm_100a by oracle/build_ref_cuda_op.sh, on the tensors of one layer's DeformFunction calls (all V views
+    # stacked on the batch axis), beside our drop-in op on the SAME tensors and the fused stage
+    ref_kernel = None
+    if world == 1:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import ref_cuda_op
+        REF = ref_cuda_op.load()
+        if REF is None:
+            ref_kernel = {"unavailable": "oracle/_ref/Deformable_ref*.so not built (no reference tree at build time)"}
+        else:
+            value, sh_, lsi_, loc, attn = ref_cuda_op.layer_call_tensors(B, V, Q, syn.PANOPTIC["levels"], device=dev)
+            vb, lb, ab = value.bfloat16(), loc.bfloat16(), attn.bfloat16()
+            ref_ms = t_ms(lambda: REF.deform_forward(value, sh_, lsi_, loc, attn, 64), 10)
+            ours32 = t_ms(lambda: mvg.deform_forward(value, sh_, lsi_, loc, attn, 64), 10)
+            ours16 = t_ms(lambda: mvg.deform_forward(vb, sh_, lsi_, lb, ab, 64), 10)
+            err = float((REF.deform_forward(value, sh_, lsi_, loc, attn, 64)
+                         - mvg.deform_forward(value, sh_, lsi_, loc, attn, 64)).abs().max())
+            ref_kernel = {
+                "reference_deform_forward_fp32_ms": ref_ms, "mvg_deform_forward_fp32_ms": ours32,
+                "mvg_deform_forward_bf16_ms": ours16, "max_abs_diff_fp32": err,
+                "fused_stage_ms": st["mean_ms"],
+                "note": "one decoder layer's sampling for all V views; the reference op ALSO needs the value GEMM output "
+                        "in fp32 plus materialised sampling_locations (118 MB) / attention_weights (59 MB) and the "
+                        "per-level grid_sample + Linears that produce them, which the fused stage includes "
+                        "(projection, G-map sampling, softmax, gather)"}
+            del value, loc, attn, vb, lb, ab
 
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -522,6 +550,7 @@ def run_ours(a):
             "launch_mode": "eager" if graphed is None else "cuda-graph replay",
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "pre_post": pre_post,
             "selected_per_layer": selected_per_layer, "all_queries_selected": worst, "parity": parity,
+            "reference_kernel": ref_kernel,
             "weight_pack_misses": prof.counters().get("weight_pack_misses", 0),
         }
         print(json.dumps(line), flush=True)

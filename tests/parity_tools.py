@@ -139,6 +139,7 @@ def _layer_report(o, ours_bounding, lay, thr, B, Q, V, exclude=None) -> Dict:
     rep["mm_ours_vs_fp32_well"] = dist_stats(ours3, o32, well)
     rep["mm_fp32_vs_fp64_well"] = dist_stats(o32, o64, well)
     rep["mm_ours_vs_fp64_well_visible"] = dist_stats(ours3, o64, well & vis)
+    rep["mm_fp32_vs_fp64_well_visible"] = dist_stats(o32, o64, well & vis)
     return rep
 
 
@@ -205,6 +206,8 @@ def summarize(rep: Dict) -> Dict:
                 ours_vs_fp32_oracle={k: worst(tf, "mm_ours_vs_fp32_well", k) for k in ("mean", "median", "p95", "max")},
                 fp32_vs_fp64_oracle={k: worst(tf, "mm_fp32_vs_fp64_well", k) for k in ("mean", "median", "p95", "max")},
                 ours_vs_fp64_oracle_visible_joints={k: worst(tf, "mm_ours_vs_fp64_well_visible", k)
+                                                    for k in ("mean", "median", "p95", "max")},
+                fp32_vs_fp64_oracle_visible_joints={k: worst(tf, "mm_fp32_vs_fp64_well_visible", k)
                                                     for k in ("mean", "median", "p95", "max")})),
         mm_free_running_last_layer=dict(
             ours_vs_fp64_oracle={k: fr[-1]["mm_ours_vs_fp64"][k] for k in ("mean", "median", "p95", "max")},
