@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--views", type=int, default=5)
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--batch8", type=int, default=8,
+                    help="frames per step of the extra frame-sharded measurement (configs[2]); 0 = skip")
     ap.add_argument("--threshold", type=float, default=0.1)
     ap.add_argument("--gemm", default=None, choices=[None, "tcgen05", "cublas"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -346,38 +348,75 @@ def run_ours(a):
     value = B * Q * a.steps / (total_ms * 1e-3)
 
     # ---- end to end: pinned host buffers in, poses + scores out, every step.
+    # Per frame the HOST supplies the pyramid (103 MB); the queries are model parameters and are built
+    # on the device by mvg.QueryInit (what DyanmicQueryTransformer.forward does per frame,
+    # dq_transformer.py:394-432).  N > 1: every rank uploads 1/N of the pyramid bytes and the ranks
+    # all-gather the rest over NVLink (sharding.PyramidExchange, its own communicator).
     # Two-deep software pipeline (what a serving loop does): while frame i runs on the compute
-    # stream, frame i+1's inputs are uploaded on a copy stream into the second graph's static
-    # buffers; every frame's inputs cross PCIe and every frame's result is read back on the host.
+    # stream, frame i+1's inputs arrive on a copy stream into the second graph's static buffers.
     e2e = None
+    g2 = None
     if not a.no_e2e:
-        h2d = sum(t.numel() * t.element_size() for t in list(host.values()) + host_feats)
+        qi = mvg.QueryInit(Q, J, 256, sc["space_size"], sc["space_center"])
+        with torch.no_grad():
+            qi.joint_embedding.weight.copy_(sc["joint_embedding"])
+            qi.instance_embedding.weight.copy_(sc["instance_embedding"])
+        qi = qi.to(dev)
         n_buf = 2 if graphed is not None else 1
         out_pose = [torch.empty((B, Q * J, 3), dtype=torch.float32).pin_memory() for _ in range(n_buf)]
         out_prob = [torch.empty((B, Q, 2), dtype=torch.float32).pin_memory() for _ in range(n_buf)]
+        q0, q1 = sharding.shard_bounds(Q, rank, world)
         if graphed is not None:
             from mvgformer_b200.graphs import GraphedDecoder
-            g2 = GraphedDecoder(dec, d["tgt"], d["reference_points"], feats, meta, shapes, lsi,
-                                d["query_pos"], threshold=a.threshold,
-                                shard=(rank, world, None) if world > 1 else None, num_queries=Q, joints=J)
-            graphs = [graphed, g2]
+            xgroup = dist.new_group(backend="nccl") if world > 1 else None
+            exch = [sharding.PyramidExchange(feats, rank, world, dev, group=xgroup) for _ in range(2)] \
+                if world > 1 else None
+            if world > 1:                      # the graphs read the all-gather targets in place
+                for ex in exch:
+                    for full, f in zip(ex.full, feats):
+                        full.copy_(f)
+                graphs = [GraphedDecoder(dec, d["tgt"], d["reference_points"], feats, meta, shapes, lsi,
+                                         d["query_pos"], threshold=a.threshold, shard=(rank, world, None),
+                                         num_queries=Q, joints=J, static_feats=ex.full) for ex in exch]
+                g2 = graphs
+                full_q = [[torch.empty((B, Q * J, c), dtype=torch.float32, device=dev) for c in (256, 256, 3)]
+                          for _ in range(2)]
+            else:
+                g2 = GraphedDecoder(dec, d["tgt"], d["reference_points"], feats, meta, shapes, lsi,
+                                    d["query_pos"], threshold=a.threshold, num_queries=Q, joints=J)
+                graphs = [graphed, g2]
             copy_stream = torch.cuda.Stream()
             h2d_done = [torch.cuda.Event() for _ in range(2)]
             compute_done = [torch.cuda.Event() for _ in range(2)]
             d2h_done = [torch.cuda.Event() for _ in range(2)]
             state = {"step": 0}
             checksum = {"v": 0.0}
+            h2d = exch[0].h2d_bytes() if world > 1 else sum(t.numel() * t.element_size() for t in host_feats)
 
             def e2e_step():
                 s_ = state["step"]
                 b_ = s_ & 1
+                g_ = graphs[b_]
                 main = torch.cuda.current_stream()
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(compute_done[b_])      # buffers of frame s-2 are free
-                    graphs[b_].load_inputs(host["tgt"], host["reference_points"], host_feats, host["query_pos"])
+                    if world > 1:
+                        exch[b_].upload_shard(host_feats)
+                        exch[b_].allgather()
+                    else:
+                        for dst, src in zip(g_.s_feats, host_feats):
+                            dst.copy_(src, non_blocking=True)
                     h2d_done[b_].record(copy_stream)
+                with torch.no_grad():
+                    if world > 1:
+                        tq, qp, rf = qi(B, out=tuple(full_q[b_]))
+                        g_.s_tgt.copy_(tq[:, q0 * J:q1 * J])
+                        g_.s_qpos.copy_(qp[:, q0 * J:q1 * J])
+                        g_.s_ref.copy_(rf[:, q0 * J:q1 * J])
+                    else:
+                        qi(B, out=(g_.s_tgt, g_.s_qpos, g_.s_ref))
                 main.wait_event(h2d_done[b_])
-                out = graphs[b_].replay()
+                out = g_.replay()
                 out_pose[b_].copy_(out[0], non_blocking=True)
                 out_prob[b_].copy_(out[1], non_blocking=True)
                 compute_done[b_].record(main)
@@ -391,9 +430,14 @@ def run_ours(a):
                 torch.cuda.synchronize()
                 checksum["v"] += float(out_prob[(state["step"] - 1) & 1][0, 0, 1])
         else:
+            h2d = sum(t.numel() * t.element_size() for t in host_feats)
+
             def e2e_step():
-                inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
                 fts = [s.to(dev, non_blocking=True) for s in host_feats]
+                with torch.no_grad():
+                    tq, qp, rf = qi(B)
+                inp = {"tgt": tq[:, q0 * J:q1 * J].contiguous(), "query_pos": qp[:, q0 * J:q1 * J].contiguous(),
+                       "reference_points": rf[:, q0 * J:q1 * J].contiguous()}
                 poses, prob = forward(inp, fts, check=True)   # result consumed on the host
                 out_pose[0].copy_(poses, non_blocking=True)
                 out_prob[0].copy_(prob, non_blocking=True)
@@ -405,9 +449,11 @@ def run_ours(a):
         for _ in range(3):
             e2e_step()
         e2e_drain()
-
-        def e2e_all():
-            e2e_step()
+        # the device-built queries must equal the scene's (same embedding tables): the two arms run the same step
+        if graphed is not None:
+            if not (torch.equal(graphs[0].s_tgt, d["tgt"]) and torch.equal(graphs[0].s_qpos, d["query_pos"])
+                    and torch.allclose(graphs[0].s_ref, d["reference_points"], atol=1e-3)):
+                raise SystemExit("bench: QueryInit does not reproduce the scene's queries")
         barrier()
         t0 = time.perf_counter()
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -419,18 +465,55 @@ def run_ours(a):
         torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - t0) * 1e3
         ms_t = torch.tensor([max(s_ev.elapsed_time(e_ev), wall_ms)], device=dev, dtype=torch.float64)
+        h2d_t = torch.tensor([float(h2d)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(h2d_t, op=dist.ReduceOp.SUM)
         barrier()
         e2e_ms = float(ms_t.item())
         if graphed is not None and world > 1 and (graphs[0].empty_scene_layers() or graphs[1].empty_scene_layers()):
             raise SystemExit("bench: empty-scene slow path hit on synthetic data (unexpected)")
         e2e = {"value": B * Q * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d),
+               "h2d_bytes_per_step": int(h2d_t.item()),
                "d2h_bytes_per_step": int(out_pose[0].numel() * 4 + out_prob[0].numel() * 4),
                "ms_per_step": e2e_ms / a.steps,
-               "pipeline": "2-deep: H2D of frame i+1 overlaps compute of frame i" if graphed is not None
+               "inputs": "pyramid from pinned host memory (whole job: every byte crosses PCIe once"
+                         + (f", 1/{world} per rank, NCCL all-gather over NVLink for the rest)" if world > 1 else ")")
+                         + "; tgt / query_pos / reference points built on the device by mvg_init_queries",
+               "pipeline": "2-deep: input hand-off of frame i+1 overlaps compute of frame i" if graphed is not None
                else "none (eager)"}
+
+    # ---- configs[2]: 8 frames per step.  The query-sharded mode replicates the pyramid work of all 8 frames on
+    # every rank; frames are independent, so the deployment mode is FRAME sharding (replicas, one all-gather of
+    # the poses) - measured here beside the headline number at every N that divides 8.
+    batch8 = None
+    if a.batch8 > 0 and a.batch8 % world == 0 and graphed is not None:
+        B8 = a.batch8
+        sc8 = syn.make_scene(batch=B8, n_views=V, num_instance=Q, seed=0, feat_dtype=torch.bfloat16)
+        b0, b1 = sharding.shard_frames(B8, rank, world)
+        Bl = b1 - b0
+        f8 = [s.to(dev) for s in sharding.select_frames(sc8["src_views"], B8, b0, b1)]
+        m8 = [{"camera": {k: v[b0:b1].to(dev) for k, v in m["camera"].items()}, "center": m["center"][b0:b1].to(dev),
+               "scale": m["scale"][b0:b1].to(dev), "inv_affine_trans": m["inv_affine_trans"][b0:b1].to(dev)}
+              for m in sc8["meta"]]
+        t8 = {k: sc8[k][b0:b1].to(dev) for k in ("tgt", "query_pos", "reference_points")}
+        del sc8
+        g8 = GraphedDecoder(dec, t8["tgt"], t8["reference_points"], f8, m8, shapes, lsi, t8["query_pos"],
+                            threshold=a.threshold, num_queries=Q, joints=J)
+        gathered = torch.empty((world, Bl, Q * J, 3), dtype=torch.float32, device=dev) if world > 1 else None
+
+        def step8():
+            out = g8()
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, out[0])
+        for _ in range(3):
+            step8()
+        n8 = max(3, min(a.steps, 10))
+        ms8 = timed(step8, n8)
+        batch8 = {"frames_per_step": B8, "frames_per_rank": Bl, "sharding": "frames (replicas) + one all-gather of poses",
+                  "value": B8 * Q * n8 / (ms8 * 1e-3), "unit": UNIT, "ms_per_step": ms8 / n8, "steps": n8}
+        g8.release()
+        del g8, f8, t8, gathered
 
     # ---- roofline of the dominant kernel (fused projection + sampling), live CUDA events
     n_pts = ql * J
@@ -550,19 +633,24 @@ def run_ours(a):
             "launch_mode": "eager" if graphed is None else "cuda-graph replay",
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "pre_post": pre_post,
             "selected_per_layer": selected_per_layer, "all_queries_selected": worst, "parity": parity,
-            "reference_kernel": ref_kernel,
+            "reference_kernel": ref_kernel, "batch8_frame_sharded": batch8,
             "weight_pack_misses": prof.counters().get("weight_pack_misses", 0),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        # dist.destroy_process_group() dead-locks while CUDA graphs that captured NCCL work are still
-        # alive (observed on 2 x B200: the JSON line is out, the call never returns).  All ranks
-        # rendezvous, flush and leave without tearing the communicator down.
+        # captured graphs hold NCCL work: release them BEFORE the communicator goes away (round 1 left
+        # with os._exit because destroy_process_group() dead-locked with live graphs)
+        sys.stdout.flush()
+        for g in ([graphed] if graphed is not None else []) + (g2 if isinstance(g2, list) else []):
+            g.release()
+        torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        guard = threading.Timer(60.0, lambda: os._exit(0))      # safety net only; not the normal path
+        guard.daemon = True
+        guard.start()
+        dist.destroy_process_group()
+        guard.cancel()
 
 
 def main():

@@ -299,6 +299,83 @@ MVG_API int mvg_nearby_joints_nms(const float* pred, const int32_t* valid_ids, c
                           int num_nearby_joints_thr, uint32_t* workspace, int32_t* keep_compact,
                           int32_t* keep_query, int32_t* keep_count, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Whole-path drivers (no torch, no Python): the launch sequence of one DQDecoderLayer.forward
+ * (eval, indices=None; lib/models/dq_decoder.py:850-1045) and of DQDecoder.forward with
+ * return_intermediate=True (:1107-1172) on a caller-provided workspace.  Only the shipped
+ * configuration is built (feature_update_method='MLP', open_forward_ffn, 3-layer offset_net,
+ * d_model 256, 8 heads x 8 points, module n_levels 1).
+ */
+typedef struct {
+  int batch, views, queries, joints, layers;      /* B, V, Q, J, L */
+  int num_levels;                                 /* Lv */
+  int level_h[MVG_MAX_LEVELS], level_w[MVG_MAX_LEVELS];
+  float img_w, img_h;                             /* NETWORK.IMAGE_SIZE */
+  float threshold;                                /* query filter, dq_decoder.py:596-612 */
+  int filter_query;                               /* 1: prob[...,1] > threshold; 0: all queries */
+  int local_min_one;                              /* 1: apply the "always one query" rule (:620-623) here;
+                                                     0: query-sharded rank (rule applied after the global count) */
+  int d_ffn;                                      /* multiple of 256 */
+} MvgDecoderConfig;
+
+/* Device pointers to one layer's operands as mvgformer_b200 packs them: GEMM weights bf16 row-major
+ * (nn.Linear layout), biases / LayerNorm parameters / class head fp32. */
+typedef struct {
+  const void* w_q;  const float* b_q;             /* [sampling_offsets; attention_weights] (192,256), (192) */
+  const void* w_o;  const float* b_o;             /* proj_attn.output_proj (256,256) */
+  const void* w_fu; const float* b_fu;            /* feature_update_mlp */
+  const float* g2;  const float* e2;  float eps2; /* norm2 */
+  const void* w1;   const float* b1;              /* linear1 (d_ffn,256) */
+  const void* w2;   const float* b2;              /* linear2 (256,d_ffn) */
+  const float* g3;  const float* e3;  float eps3; /* norm3 */
+  const float* wc;  const float* bc;              /* class_embed (2,256), (2) fp32 */
+  const void* w_m1; const float* b_m1;            /* pose_embed.MLP.layers.0 */
+  const void* w_m2; const float* b_m2;            /* pose_embed.MLP.layers.1 */
+  const void* w_m3; const float* b_m3;            /* pose_embed.MLP.layers.2 zero-padded to (16,256), (16) */
+} MvgLayerWeights;
+
+/* Bytes of `workspace` for mvg_decoder / mvg_decoder_layer (pyramid_is_nchw: the pyramid arrives as
+ * NCHW levels and is transposed into the workspace first).  -1 on a bad configuration. */
+MVG_API int64_t mvg_decoder_workspace_bytes(const MvgDecoderConfig* cfg, int pyramid_is_nchw);
+
+/* One layer on pre-projected maps: value_hm / gmap point at THIS layer's 8 heads / 192 columns of the
+ * mvg_value_proj_gemm outputs (ld_g, value_head_stride as in MvgSampleParams).  cams from
+ * mvg_pack_cameras.  tgt, query_pos (B,N,256), ref3d (B,N,3) fp32 in; outputs = the layer's 5-tuple:
+ * tgt_out (B,N,256), ref_out (B,N,3), refined_abs / projs_abs (B,V,N,2), class_prob (B,Q,2);
+ * selected_count (1 int32, may be NULL) = queries selected here.  workspace: 256-byte aligned,
+ * >= mvg_decoder_workspace_bytes(cfg, 0). */
+MVG_API int mvg_decoder_layer(const MvgDecoderConfig* cfg, const MvgLayerWeights* w, const void* value_hm,
+                      const void* gmap, int ld_g, int64_t value_head_stride, const float* cams,
+                      const float* tgt, const float* query_pos, const float* ref3d, float* tgt_out,
+                      float* ref_out, float* refined_abs, float* projs_abs, float* class_prob,
+                      int32_t* selected_count, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The L-layer decoder.  layers: HOST array of L MvgLayerWeights; w_vg_all (L*448,256) bf16 = per layer
+ * [rayconv | sampling_offsets | attention_weights], b_vg_all (L*448) fp32 (zeros for the last 192 of
+ * every layer: their bias rides in b_q).  Pyramid: EITHER pyramid_levels (HOST array of Lv device
+ * pointers to (V*B, 256, H_l, W_l) maps of dtype pyramid_dtype) OR pyramid_cl ((V*B, S, 256) bf16,
+ * consumed in place); the other one NULL.  Outputs (return_intermediate): hs (L,B,N,256),
+ * refs (L,B,N,3), refs2d / projs2d (L,B,V,N,2), class_probs (L,B,Q,2), selected_counts (L) int32
+ * or NULL. */
+MVG_API int mvg_decoder(const MvgDecoderConfig* cfg, const MvgLayerWeights* layers, const void* w_vg_all,
+                const float* b_vg_all, const void* const* pyramid_levels, int pyramid_dtype,
+                const void* pyramid_cl, const float* cams, const float* tgt, const float* query_pos,
+                const float* ref3d, float* hs, float* refs, float* refs2d, float* projs2d,
+                float* class_probs, int32_t* selected_counts, void* workspace, int64_t workspace_bytes,
+                void* stream);
+
+/* Exchange step of the query-sharded mode: ONE all-gather of every rank's final
+ * poses (B, Ql*J, 3), class prob (B, Ql, 2) and per-layer selected counts (L) -> poses (B, Q*J, 3),
+ * prob (B, Q, 2), counts (L) fp32 = global per-layer counts, identical on every rank.  Ranks own
+ * contiguous query blocks whose sizes differ by at most one (rank r: Q/world + (r < Q % world)).
+ * nccl_comm: the caller's ncclComm_t (ignored for world == 1); ncclAllGather is resolved at run time from
+ * the NCCL library already loaded in the process.  workspace: mvg_allgather_poses_workspace_bytes. */
+MVG_API int64_t mvg_allgather_poses_workspace_bytes(int batch, int queries, int joints, int layers, int world);
+MVG_API int mvg_allgather_poses(void* nccl_comm, int rank, int world, const float* poses_local,
+                        const float* prob_local, const int32_t* counts_local, int batch, int queries,
+                        int joints, int layers, float* poses, float* prob, float* counts,
+                        void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ MVG_F32, MVG_BF16, MVG_F64, MVG_F16 = 0, 1, 2, 3
 MVG_CAM_FIELDS = 11
 MVG_MAX_LEVELS = 4
 MVG_CAM_FLOATS = 64
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class MvgError(RuntimeError):
@@ -33,6 +33,23 @@ class MvgSampleParams(C.Structure):
                 ("level_start", C.c_int * MVG_MAX_LEVELS),
                 ("spatial_size", C.c_int), ("ld_g", C.c_int),
                 ("img_w", C.c_float), ("img_h", C.c_float), ("value_head_stride", C.c_int64)]
+
+
+class MvgDecoderConfig(C.Structure):
+    _fields_ = [("batch", C.c_int), ("views", C.c_int), ("queries", C.c_int), ("joints", C.c_int),
+                ("layers", C.c_int), ("num_levels", C.c_int),
+                ("level_h", C.c_int * MVG_MAX_LEVELS), ("level_w", C.c_int * MVG_MAX_LEVELS),
+                ("img_w", C.c_float), ("img_h", C.c_float), ("threshold", C.c_float),
+                ("filter_query", C.c_int), ("local_min_one", C.c_int), ("d_ffn", C.c_int)]
+
+
+class MvgLayerWeights(C.Structure):
+    _fields_ = [("w_q", C.c_void_p), ("b_q", C.c_void_p), ("w_o", C.c_void_p), ("b_o", C.c_void_p),
+                ("w_fu", C.c_void_p), ("b_fu", C.c_void_p), ("g2", C.c_void_p), ("e2", C.c_void_p),
+                ("eps2", C.c_float), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p),
+                ("b2", C.c_void_p), ("g3", C.c_void_p), ("e3", C.c_void_p), ("eps3", C.c_float),
+                ("wc", C.c_void_p), ("bc", C.c_void_p), ("w_m1", C.c_void_p), ("b_m1", C.c_void_p),
+                ("w_m2", C.c_void_p), ("b_m2", C.c_void_p), ("w_m3", C.c_void_p), ("b_m3", C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -60,6 +77,11 @@ SIGNATURES = {
     "mvg_init_queries": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "mvg_assemble_predictions": [_P, _P, _I, _I, _I, _F, _P, _P, _P, _P],
     "mvg_pack_cameras": [_P, _P, _I, _I, _F, _F, _P, _P],
+    "mvg_decoder_layer": [C.POINTER(MvgDecoderConfig), C.POINTER(MvgLayerWeights), _P, _P, _I, _L, _P, _P, _P, _P,
+                          _P, _P, _P, _P, _P, _P, _P, _L, _P],
+    "mvg_decoder": [C.POINTER(MvgDecoderConfig), C.POINTER(MvgLayerWeights), _P, _P, _P, _I, _P, _P, _P, _P, _P,
+                    _P, _P, _P, _P, _P, _P, _P, _L, _P],
+    "mvg_allgather_poses": [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "mvg_nearby_joints_nms": [_P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P],
 }
 
@@ -80,6 +102,10 @@ def load() -> C.CDLL:
     lib.mvg_last_error.argtypes = []
     lib.mvg_abi_version.restype = C.c_int
     lib.mvg_launch_count.restype = C.c_int64
+    lib.mvg_decoder_workspace_bytes.restype = C.c_int64
+    lib.mvg_decoder_workspace_bytes.argtypes = [C.POINTER(MvgDecoderConfig), C.c_int]
+    lib.mvg_allgather_poses_workspace_bytes.restype = C.c_int64
+    lib.mvg_allgather_poses_workspace_bytes.argtypes = [C.c_int] * 5
     lib.mvg_project_sample_workspace_bytes.restype = C.c_int64
     lib.mvg_project_sample_workspace_bytes.argtypes = [C.POINTER(MvgSampleParams)]
     for name, args in SIGNATURES.items():

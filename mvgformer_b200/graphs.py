@@ -22,7 +22,7 @@ class GraphedDecoder:
     def __init__(self, decoder, tgt, reference_points, src_views: Sequence[torch.Tensor], meta,
                  spatial_shapes, level_start_index, query_pos, *, threshold: float,
                  shard: Optional[tuple] = None, num_queries: Optional[int] = None, joints: int = 15,
-                 warmup: int = 2):
+                 warmup: int = 2, static_feats: Optional[Sequence[torch.Tensor]] = None):
         self.decoder = decoder
         self.threshold = threshold
         self.shard = shard
@@ -30,7 +30,8 @@ class GraphedDecoder:
         self.s_tgt = tgt.clone()
         self.s_ref = reference_points.clone()
         self.s_qpos = query_pos.clone()
-        self.s_feats = [s.clone() for s in src_views]
+        # static_feats: caller-owned input buffers (e.g. the all-gather target of sharding.PyramidExchange)
+        self.s_feats = [s.clone() for s in src_views] if static_feats is None else list(static_feats)
         self.num_queries, self.joints = num_queries, joints
         self.graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
@@ -81,6 +82,12 @@ class GraphedDecoder:
     def replay(self):
         self.graph.replay()
         return self.out
+
+    def release(self) -> None:
+        """Drops the captured graph (and the NCCL work it holds) - call before tearing the process
+        group down."""
+        self.graph.reset()
+        self.out = None
 
     def empty_scene_layers(self) -> List[int]:
         """Sharded mode only (host sync): layers in which no rank selected any query - the

@@ -18,7 +18,7 @@ from torch import nn
 
 from . import _lib
 from ._lib import check, stream_ptr
-from .synthetic import TPOSE_MM
+from .tpose import TPOSE_MM
 
 
 class QueryInit(nn.Module):
@@ -46,17 +46,26 @@ class QueryInit(nn.Module):
         n = math.ceil(pow(num_instance, 1 / 2.0))                                            # :301
         self.register_buffer("_lin", torch.linspace(0., 1., n), persistent=False)            # :302
 
-    def forward(self, batch: int):
-        """-> tgt (B, Q*J, C), query_pos (B, Q*J, C), reference_points (B, Q*J, 3) fp32."""
+    def forward(self, batch: int, out=None):
+        """-> tgt (B, Q*J, C), query_pos (B, Q*J, C), reference_points (B, Q*J, 3) fp32.
+        `out` = (tgt, query_pos, reference_points) pre-allocated contiguous fp32 CUDA tensors to write
+        into (e.g. the static input buffers of a captured decoder graph)."""
         w = self.joint_embedding.weight
         if not w.is_cuda:
             raise RuntimeError("Not implemented on the CPU")
         lib = _lib.load()
         Q, J, C = self.num_instance, self.num_joints, self.hidden_dim
         dev = w.device
-        tgt = torch.empty((batch, Q * J, C), dtype=torch.float32, device=dev)
-        qpos = torch.empty((batch, Q * J, C), dtype=torch.float32, device=dev)
-        ref = torch.empty((batch, Q * J, 3), dtype=torch.float32, device=dev)
+        if out is not None:
+            tgt, qpos, ref = out
+            for t, last in ((tgt, C), (qpos, C), (ref, 3)):
+                if t.shape != (batch, Q * J, last) or t.dtype != torch.float32 or not t.is_contiguous() \
+                        or t.device != dev:
+                    raise _lib.MvgError("QueryInit: `out` tensors must be contiguous fp32 (B, Q*J, C | 3) on the module's device")
+        else:
+            tgt = torch.empty((batch, Q * J, C), dtype=torch.float32, device=dev)
+            qpos = torch.empty((batch, Q * J, C), dtype=torch.float32, device=dev)
+            ref = torch.empty((batch, Q * J, 3), dtype=torch.float32, device=dev)
         import ctypes as Cc
         # module.float() / .half() / .to(dtype) also cast the buffers: hand the kernel the dtypes it reads
         lin = self._lin.detach().to(device=dev, dtype=torch.float32).contiguous()

@@ -17,7 +17,7 @@ collectives are the only thing this module does - tests/test_sharding_gloo.py).
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -122,3 +122,62 @@ def sharded_decoder_forward(decoder, tgt, reference_points, src_views, meta, spa
             if not empty:
                 break
     return poses, prob
+
+
+class PyramidExchange:
+    """Input hand-off for N ranks of one box: every rank copies 1/N of the frame's pyramid bytes from
+    (pinned) host memory and the ranks all-gather the rest over NVLink, instead of N full uploads
+    through the shared host links (the pyramid is replicated on every rank: each rank's queries
+    project anywhere in every view).  Works on any dtype / backend (`gloo` on CPU tensors in the tests).
+
+    `levels`: example tensors (shapes / dtype of the full per-level maps).  `full[l]` are this rank's
+    static device tensors (views into one flat buffer per level, padded to a multiple of `world`)."""
+
+    def __init__(self, levels: Sequence[torch.Tensor], rank: int, world: int, device, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.flat: List[torch.Tensor] = []
+        self.full: List[torch.Tensor] = []
+        self.span: List[Tuple[int, int, int]] = []          # (numel, shard_len, my valid length)
+        for t in levels:
+            n = t.numel()
+            shard = (n + world - 1) // world
+            shard = (shard + 7) // 8 * 8                    # 16-byte aligned slices for 2-byte types
+            buf = torch.empty(shard * world, dtype=t.dtype, device=device)
+            self.flat.append(buf)
+            self.full.append(buf[:n].view(t.shape))
+            a = min(rank * shard, n)
+            b = min(a + shard, n)
+            self.span.append((n, shard, b - a))
+
+    def h2d_bytes(self) -> int:
+        return sum(v * f.element_size() for (_, _, v), f in zip(self.span, self.flat))
+
+    def upload_shard(self, host_levels: Sequence[torch.Tensor]) -> None:
+        """Enqueues the H2D copy of THIS rank's slice of every level on the current stream."""
+        for (n, shard, valid), buf, h in zip(self.span, self.flat, host_levels):
+            if valid > 0:
+                a = self.rank * shard
+                buf[a:a + valid].copy_(h.reshape(-1)[a:a + valid], non_blocking=True)
+
+    def allgather(self) -> None:
+        """One all-gather per level on the current stream (in place: every rank's slice already sits
+        at its final offset of the flat buffer)."""
+        if self.world == 1:
+            return
+        for (n, shard, valid), buf in zip(self.span, self.flat):
+            mine = buf[self.rank * shard:(self.rank + 1) * shard]
+            dist.all_gather_into_tensor(buf, mine, group=self.group)
+
+
+def shard_frames(batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Frame sharding (replicas only, no exchange inside the decoder): frames [b0, b1) of rank `rank`."""
+    return shard_bounds(batch, rank, world)
+
+
+def select_frames(src_views: Sequence[torch.Tensor], batch: int, b0: int, b1: int) -> List[torch.Tensor]:
+    """Rows of the view-major pyramid (row = v * B + b, dq_transformer.py:352-354) of frames [b0, b1)."""
+    out = []
+    for s in src_views:
+        V = s.shape[0] // batch
+        out.append(s.view(V, batch, *s.shape[1:])[:, b0:b1].reshape(V * (b1 - b0), *s.shape[1:]).contiguous())
+    return out

@@ -22,24 +22,7 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 import torch
 
-# reference `tpose.pt` (float64, (15,3), mm) - data, printed from the reference root with
-# full float64 precision (oracle/gen_golden.py asserts bit-equality with the file)
-TPOSE_MM = np.array([
-    [-8.072000000000116, -32.55199999999991, 571.168],
-    [60.721999999999866, 149.90200000000004, 738.678],
-    [0.0, 0.0, 0.0],
-    [-164.48500000000013, 40.317999999999984, 565.1979999999998],
-    [-240.865, 30.698999999999955, 320.678],
-    [-50.100000000000136, 157.66700000000003, 396.0380000000001],
-    [-84.93000000000018, 59.38099999999997, -4.908999999999992],
-    [-85.88400000000013, 12.75, -397.528],
-    [-74.34600000000012, -30.82299999999998, -712.4110000000001],
-    [143.12999999999988, -101.28099999999995, 584.0480000000001],
-    [249.96199999999988, -103.42399999999998, 364.74799999999993],
-    [192.50199999999984, 82.17200000000003, 451.7579999999999],
-    [84.93099999999993, -59.38099999999997, 4.908999999999992],
-    [142.1819999999999, -112.16499999999996, -360.12600000000003],
-    [177.20199999999988, -227.375, -712.763]], dtype=np.float64)
+from .tpose import TPOSE_MM  # noqa: E402,F401  (re-exported: tests and fixtures import it from here)
 
 PANOPTIC = dict(orig_size=(1920, 1080), net_size=(960, 512),
                 levels=((128, 240), (64, 120), (32, 60)),
@@ -169,10 +152,15 @@ def make_pyramid(batch: int, n_views: int, levels, rng: np.random.Generator,
 
 
 def make_queries(batch: int, num_instance: int, num_joints: int, rng, d_model=256,
-                 dtype=torch.float32, device="cpu") -> Tuple[torch.Tensor, torch.Tensor]:
-    """tgt / query_pos = halves of (joint_emb + instance_emb), dq_transformer.py:394-432."""
+                 dtype=torch.float32, device="cpu", embeddings: Dict = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """tgt / query_pos = halves of (joint_emb + instance_emb), dq_transformer.py:394-432.
+    `embeddings` (optional dict) receives the two embedding tables (the QueryInit weights that
+    reproduce tgt / query_pos)."""
     joint = rng.standard_normal((num_joints, 2 * d_model), dtype=np.float32)
     inst = rng.standard_normal((num_instance, 2 * d_model), dtype=np.float32)
+    if embeddings is not None:
+        embeddings["joint_embedding"] = torch.from_numpy(joint.copy())
+        embeddings["instance_embedding"] = torch.from_numpy(inst.copy())
     emb = (joint[None] + inst[:, None]).reshape(num_instance * num_joints, 2 * d_model)
     emb = torch.from_numpy(emb)
     query_pos, tgt = emb[:, :d_model], emb[:, d_model:]
@@ -274,7 +262,8 @@ def make_scene(cfg=PANOPTIC, *, batch=1, n_views=5, num_instance=1024, num_joint
                                  center=cfg["space_center"])
     meta = make_meta(cams, batch, cfg["orig_size"], cfg["net_size"], device=device)
     feats = make_pyramid(batch, n_views, levels, rng, dtype=feat_dtype, device=device)
-    tgt, query_pos = make_queries(batch, num_instance, num_joints, rng, device=device)
+    emb: Dict = {}
+    tgt, query_pos = make_queries(batch, num_instance, num_joints, rng, device=device, embeddings=emb)
     ref = make_reference_points(batch, num_instance, cfg["space_size"], cfg["space_center"],
                                 device=device)
     shapes, lsi = spatial_shapes_tensors(levels, device=device)
@@ -282,4 +271,5 @@ def make_scene(cfg=PANOPTIC, *, batch=1, n_views=5, num_instance=1024, num_joint
                 reference_points=ref, spatial_shapes=shapes, level_start_index=lsi,
                 img_size=list(cfg["net_size"]), space_size=list(cfg["space_size"]),
                 space_center=list(cfg["space_center"]), n_views=n_views, batch=batch,
-                num_instance=num_instance, num_joints=num_joints)
+                num_instance=num_instance, num_joints=num_joints,
+                joint_embedding=emb["joint_embedding"], instance_embedding=emb["instance_embedding"])

@@ -27,7 +27,8 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/mvg_b200.h but not exported"
     assert set(_lib.SIGNATURES) | {"mvg_last_error", "mvg_abi_version", "mvg_launch_count",
-                                   "mvg_project_sample_workspace_bytes"} == set(syms)
+                                   "mvg_project_sample_workspace_bytes", "mvg_decoder_workspace_bytes",
+                                   "mvg_allgather_poses_workspace_bytes"} == set(syms)
     assert _lib.load().mvg_abi_version() == _lib.ABI_VERSION
 
 
@@ -143,6 +144,34 @@ def test_sample_params_struct_matches_header():
             names.append(re.sub(r"\[.*?\]", "", part.split()[-1]).strip())
     assert names == [n for n, _ in _lib.MvgSampleParams._fields_], (names, _lib.MvgSampleParams._fields_)
     assert ctypes.sizeof(_lib.MvgSampleParams) == 4 * 20 + 8
+
+
+def test_driver_structs_match_header():
+    """ctypes mirrors of MvgDecoderConfig / MvgLayerWeights: field names and order as declared."""
+    text = open(os.path.join(ROOT, "include", "mvg_b200.h")).read()
+    for name, mirror in (("MvgDecoderConfig", _lib.MvgDecoderConfig), ("MvgLayerWeights", _lib.MvgLayerWeights)):
+        body = re.search(r"typedef struct \{([^{}]*)\} %s;" % name, text).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                names.append(re.sub(r"\[.*?\]", "", part.split()[-1]).replace("*", "").strip())
+        assert names == [n for n, _ in mirror._fields_], (name, names)
+    assert ctypes.sizeof(_lib.MvgDecoderConfig) == 4 * 20
+    cfg = _lib.MvgDecoderConfig(batch=1, views=5, queries=1024, joints=15, layers=4, num_levels=3, d_ffn=1024,
+                                img_w=960.0, img_h=512.0, threshold=0.1, filter_query=1, local_min_one=1)
+    for i, (h, w) in enumerate(syn.PANOPTIC["levels"]):
+        cfg.level_h[i], cfg.level_w[i] = h, w
+    lib = _lib.load()
+    n_cl = lib.mvg_decoder_workspace_bytes(ctypes.byref(cfg), 0)
+    n_nchw = lib.mvg_decoder_workspace_bytes(ctypes.byref(cfg), 1)
+    assert n_nchw - n_cl >= 5 * 40320 * 256 * 2 and n_cl > 5 * 40320 * 448 * 4 * 2      # maps of 4 layers, fp16
+    cfg.d_ffn = 1000
+    assert lib.mvg_decoder_workspace_bytes(ctypes.byref(cfg), 0) == -1
+    assert lib.mvg_allgather_poses_workspace_bytes(1, 1024, 15, 4, 8) >= 9 * (128 * 47 + 4) * 4
 
 
 def test_missing_library_fails_loudly():

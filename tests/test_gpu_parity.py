@@ -766,3 +766,36 @@ def test_cameras_are_not_cached_by_address():
     assert torch.equal(out_b, want_b)
     assert not torch.equal(out_b, out_a)
     assert recycled or True      # (informational: the allocator normally hands the same block back)
+
+
+# ----------------------------------------------------------------------------- query sharding on one GPU
+@pytest.mark.parametrize("world", [2, 3])
+def test_query_sharded_blocks_equal_unsharded(world):
+    """The N > 1 path without a second GPU: every rank's contiguous query block is run through
+    DQDecoder.forward(shard=(rank, world, ...)) on this device, the blocks are concatenated like the
+    final all-gather does, and the result must be BIT-identical to the unsharded decoder (queries do
+    not interact; per-layer counts add up to the global selection)."""
+    from mvgformer_b200 import sharding
+    L, B, V, Q, J, thr = 3, 2, 3, 25, 15, 0.1          # uneven split for both world sizes
+    sc = syn.make_scene(batch=B, n_views=V, num_instance=Q, seed=3, levels=((32, 60), (16, 30), (8, 15)))
+    sd = syn.make_decoder_state_dict(L, np.random.default_rng(5))
+    dec = make_decoder(sc, sd, L)
+    scd = scene_to(sc, DEV)
+    with torch.no_grad():
+        hs, refs, r2d, p2d, cls = dec(scd["tgt"], scd["reference_points"], scd["src_views"], scd["meta"],
+                                      scd["spatial_shapes"], scd["level_start_index"], None,
+                                      query_pos=scd["query_pos"], threshold=thr)
+        poses, probs, counts = [], [], []
+        for rank in range(world):
+            t = {k: sharding.shard_points(scd[k], Q, J, rank, world) for k in ("tgt", "query_pos", "reference_points")}
+            _, refs_r, _, _, cls_r = dec(t["tgt"], t["reference_points"], scd["src_views"], scd["meta"],
+                                         scd["spatial_shapes"], scd["level_start_index"], None,
+                                         query_pos=t["query_pos"], threshold=thr, shard=(rank, world, None, None))
+            poses.append(refs_r[-1])
+            probs.append(cls_r[-1])
+            counts.append(dec.last_shard_counts.clone())
+    assert torch.equal(torch.cat(poses, 1), refs[-1])
+    assert torch.equal(torch.cat(probs, 1), cls[-1])
+    total = torch.stack(counts).sum(0).cpu()
+    want = torch.tensor([int((c[..., 1] > thr).sum()) for c in cls], dtype=total.dtype)
+    assert torch.equal(total, want) and int(total.min()) > 0
