@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true", help="skip the CUDA-vs-oracle parity block (one oracle decoder pass)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "on", "off"],
+                    help="overlap the query-independent prologue of step i+1 with the layers of step i "
+                         "(graphs.PipelinedDecoder); auto = on for N > 1")
     return ap.parse_args()
 
 
@@ -259,7 +262,17 @@ def run_ours(a):
                                  d["query_pos"], threshold=a.threshold,
                                  shard=(rank, world, None) if world > 1 else None, num_queries=Q, joints=J)
 
+    pipe = None
+    if graphed is not None and (a.pipeline == "on" or (a.pipeline == "auto" and world > 1)):
+        from mvgformer_b200.graphs import PipelinedDecoder
+        pipe = PipelinedDecoder(dec, d["tgt"], d["reference_points"], feats, meta, shapes, lsi, d["query_pos"],
+                                threshold=a.threshold, shard=(rank, world, None) if world > 1 else None,
+                                num_queries=Q, joints=J)
+
     def forward_resident():
+        if pipe is not None:
+            out = pipe.step()
+            return out[0], out[1]
         if graphed is not None:
             out = graphed()
             return out[0], out[1]
@@ -302,7 +315,7 @@ def run_ours(a):
     clocks = ClockSampler(local)
     clocks.start()
     total_ms = timed(forward_resident, a.steps)
-    if graphed is not None and graphed.empty_scene_layers():
+    if (pipe.empty_scene_layers() if pipe is not None else (graphed is not None and graphed.empty_scene_layers())):
         raise SystemExit("bench: empty-scene slow path hit on synthetic data (unexpected)")
     prof.enable(False)
     clk = clocks.stop()
@@ -588,13 +601,13 @@ def run_ours(a):
         if REF is None:
             ref_kernel = {"unavailable": "oracle/_ref/Deformable_ref*.so not built (no reference tree at build time)"}
         else:
-            value, sh_, lsi_, loc, attn = ref_cuda_op.layer_call_tensors(B, V, Q, syn.PANOPTIC["levels"], device=dev)
-            vb, lb, ab = value.bfloat16(), loc.bfloat16(), attn.bfloat16()
-            ref_ms = t_ms(lambda: REF.deform_forward(value, sh_, lsi_, loc, attn, 64), 10)
-            ours32 = t_ms(lambda: mvg.deform_forward(value, sh_, lsi_, loc, attn, 64), 10)
+            rvalue, sh_, lsi_, loc, attn = ref_cuda_op.layer_call_tensors(B, V, Q, syn.PANOPTIC["levels"], device=dev)
+            vb, lb, ab = rvalue.bfloat16(), loc.bfloat16(), attn.bfloat16()
+            ref_ms = t_ms(lambda: REF.deform_forward(rvalue, sh_, lsi_, loc, attn, 64), 10)
+            ours32 = t_ms(lambda: mvg.deform_forward(rvalue, sh_, lsi_, loc, attn, 64), 10)
             ours16 = t_ms(lambda: mvg.deform_forward(vb, sh_, lsi_, lb, ab, 64), 10)
-            err = float((REF.deform_forward(value, sh_, lsi_, loc, attn, 64)
-                         - mvg.deform_forward(value, sh_, lsi_, loc, attn, 64)).abs().max())
+            err = float((REF.deform_forward(rvalue, sh_, lsi_, loc, attn, 64)
+                         - mvg.deform_forward(rvalue, sh_, lsi_, loc, attn, 64)).abs().max())
             ref_kernel = {
                 "reference_deform_forward_fp32_ms": ref_ms, "mvg_deform_forward_fp32_ms": ours32,
                 "mvg_deform_forward_bf16_ms": ours16, "max_abs_diff_fp32": err,
@@ -603,7 +616,7 @@ def run_ours(a):
                         "in fp32 plus materialised sampling_locations (118 MB) / attention_weights (59 MB) and the "
                         "per-level grid_sample + Linears that produce them, which the fused stage includes "
                         "(projection, G-map sampling, softmax, gather)"}
-            del value, loc, attn, vb, lb, ab
+            del rvalue, loc, attn, vb, lb, ab
 
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -630,7 +643,8 @@ def run_ours(a):
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(a, world),
             "gemm_backend": mlinear.get_backend(), "gpu_launches": int(launches_per_step),
-            "launch_mode": "eager" if graphed is None else "cuda-graph replay",
+            "launch_mode": "eager" if graphed is None else ("cuda-graph replay, prologue of step i+1 (pyramid hand-off + "
+                           "value GEMM) overlapped with the layers of step i" if pipe is not None else "cuda-graph replay"),
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "pre_post": pre_post,
             "selected_per_layer": selected_per_layer, "all_queries_selected": worst, "parity": parity,
             "reference_kernel": ref_kernel, "batch8_frame_sharded": batch8,
@@ -641,7 +655,8 @@ def run_ours(a):
         # captured graphs hold NCCL work: release them BEFORE the communicator goes away (round 1 left
         # with os._exit because destroy_process_group() dead-locked with live graphs)
         sys.stdout.flush()
-        for g in ([graphed] if graphed is not None else []) + (g2 if isinstance(g2, list) else []):
+        for g in ([graphed] if graphed is not None else []) + (g2 if isinstance(g2, list) else []) + \
+                ([pipe] if pipe is not None else []):
             g.release()
         torch.cuda.synchronize()
         dist.barrier()

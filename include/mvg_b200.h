@@ -263,6 +263,19 @@ MVG_API int mvg_ffn_chain(const void* aver_bf16, const float* tgt, const void* w
                   const void* w2, const float* b2, const float* g3, const float* e3, float eps3,
                   int64_t M, int d_ffn, float* out, void* stream);
 
+/* Fused offset_net MLP (dq_decoder.py:97-111, :659-717; MLP multi_view_pose_transformer.py:81-102) on the
+ * rows of the SELECTED queries only (the reference gathers them into a padded rectangle, :899-932):
+ *   out[row, 0..2] = relu(relu(attn[row] @ W1^T + b1) @ W2^T + b2) @ W3^T + b3
+ * attn (B*V*N, 256) bf16 (output_proj result); info[0] = number of selected queries and
+ * batch_ids / query_ids = their frame / query ids (device; mvg_select_pad's info and *_rev arrays);
+ * W1, W2 (256,256) bf16, b1, b2 (256) fp32, W3 (3,256) fp32, b3 (3) fp32; out (B*V*N, out_ld) fp32:
+ * columns 0..2 of the rows of selected queries (all views, all joints) are written, nothing else.
+ * One tcgen05 kernel, hidden activations stay on chip, no host synchronisation. */
+MVG_API int mvg_offset_chain(const void* attn_bf16, const int32_t* info, const int64_t* batch_ids,
+                     const int64_t* query_ids, const void* w1, const float* b1, const void* w2,
+                     const float* b2, const float* w3, const float* b3, int batch, int views, int queries,
+                     int joints, float* out, int out_ld, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * The steps either side of the decoder.
  *
@@ -331,7 +344,7 @@ typedef struct {
   const float* wc;  const float* bc;              /* class_embed (2,256), (2) fp32 */
   const void* w_m1; const float* b_m1;            /* pose_embed.MLP.layers.0 */
   const void* w_m2; const float* b_m2;            /* pose_embed.MLP.layers.1 */
-  const void* w_m3; const float* b_m3;            /* pose_embed.MLP.layers.2 zero-padded to (16,256), (16) */
+  const float* w_m3; const float* b_m3;           /* pose_embed.MLP.layers.2 (3,256), (3) fp32 */
 } MvgLayerWeights;
 
 /* Bytes of `workspace` for mvg_decoder / mvg_decoder_layer (pyramid_is_nchw: the pyramid arrives as

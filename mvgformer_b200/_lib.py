@@ -19,7 +19,7 @@ MVG_F32, MVG_BF16, MVG_F64, MVG_F16 = 0, 1, 2, 3
 MVG_CAM_FIELDS = 11
 MVG_MAX_LEVELS = 4
 MVG_CAM_FLOATS = 64
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class MvgError(RuntimeError):
@@ -82,6 +82,7 @@ SIGNATURES = {
     "mvg_decoder": [C.POINTER(MvgDecoderConfig), C.POINTER(MvgLayerWeights), _P, _P, _P, _I, _P, _P, _P, _P, _P,
                     _P, _P, _P, _P, _P, _P, _P, _L, _P],
     "mvg_allgather_poses": [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "mvg_offset_chain": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P],
     "mvg_nearby_joints_nms": [_P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P],
 }
 

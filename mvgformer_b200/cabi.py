@@ -30,7 +30,8 @@ def pack_layer(layer) -> MvgLayerWeights:
     """MvgLayerWeights of a mvgformer_b200.DQDecoderLayer (pointers into its cached packed weights,
     which the module keeps alive)."""
     pw, lw = layer.proj_attn.packed_weights(), layer.packed_weights()
-    (m1, c1), (m2, c2), (m3, c3) = lw["mlp"]
+    (m1, c1), (m2, c2) = lw["mlp"][0], lw["mlp"][1]
+    m3, c3 = lw["head"]
     p = lambda t: t.data_ptr()
     return MvgLayerWeights(w_q=p(pw["w_q"]), b_q=p(pw["b_q"]), w_o=p(pw["w_o"]), b_o=p(pw["b_o"]),
                            w_fu=p(lw["w_fu"]), b_fu=p(lw["b_fu"]), g2=p(lw["g2"]), e2=p(lw["e2"]),

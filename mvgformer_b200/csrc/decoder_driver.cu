@@ -10,7 +10,8 @@
 //   per call : [NCHW pyramid -> channels-last bf16]  value | G maps of all layers (one tcgen05 GEMM)
 //   per layer: with_pos_embed + cast, qproj GEMM, mvg_project_sample_fused, output_proj (+ bounding
 //              mask), masked view mean, fused feature update (mvg_ffn_chain), class head, query
-//              selection, offset-net MLP (3 GEMMs), offsets -> undistort -> DLT -> zero-fill scatter.
+//              selection, fused offset-net MLP on the selected rows (mvg_offset_chain),
+//              offsets -> undistort -> DLT -> zero-fill scatter.
 // Nothing is allocated or synchronised here; every kernel is enqueued on `stream`.
 #include <dlfcn.h>
 
@@ -31,9 +32,8 @@ struct DecoderWs {
   uint8_t* bounding;     // (B, V, N)
   uint8_t* attn;         // (B, V, N, 256) bf16
   uint8_t* aver;         // (B, N, 256) bf16
-  uint8_t* h1;           // (B, V, N, 256) bf16
-  uint8_t* h2;           // (B, V, N, 256) bf16
-  float* mlp_out;        // (B*V*N, 16)
+  float* mlp_out;        // (B*V*N, 4)
+  int64_t* ids;          // 4 x (B*Q): batch / query ids, padded and reverse (mvg_select_pad)
   uint8_t* selected;     // (B, Q)
   int32_t* counts;       // (B)
   int32_t* info;         // (4)
@@ -69,9 +69,8 @@ static int64_t layout(const MvgDecoderConfig& c, bool nchw, void* base, DecoderW
   w->bounding = take(B * V * N);
   w->attn = take(B * V * N * 256 * 2);
   w->aver = take(B * N * 256 * 2);
-  w->h1 = take(B * V * N * 256 * 2);
-  w->h2 = take(B * V * N * 256 * 2);
-  w->mlp_out = reinterpret_cast<float*>(take(B * V * N * 16 * 4));
+  w->mlp_out = reinterpret_cast<float*>(take(B * V * N * 4 * 4));
+  w->ids = reinterpret_cast<int64_t*>(take(4 * B * c.queries * 8));
   w->selected = take(B * c.queries);
   w->counts = reinterpret_cast<int32_t*>(take(4 * B));
   w->info = reinterpret_cast<int32_t*>(take(16));
@@ -110,11 +109,11 @@ static int run_layer(const MvgDecoderConfig& c, const MvgSampleParams& prm, cons
                         B * N, c.d_ffn, tgt_out, stream));
   MVG_TRY(mvg_class_head(tgt_out, w.wc, w.bc, c.batch, c.queries, c.joints, prob_out, stream));
   MVG_TRY(mvg_select_pad(prob_out, c.batch, c.queries, c.threshold, c.filter_query ? 0 : 1, c.local_min_one,
-                         ws.selected, ws.counts, ws.info, nullptr, nullptr, nullptr, nullptr, stream));
-  MVG_TRY(mvg_linear_bf16(ws.attn, w.w_m1, w.b_m1, ws.h1, MVG_BF16, B * V * N, 256, 256, 256, 1, nullptr, stream));
-  MVG_TRY(mvg_linear_bf16(ws.h1, w.w_m2, w.b_m2, ws.h2, MVG_BF16, B * V * N, 256, 256, 256, 1, nullptr, stream));
-  MVG_TRY(mvg_linear_bf16(ws.h2, w.w_m3, w.b_m3, ws.mlp_out, MVG_F32, B * V * N, 16, 256, 16, 0, nullptr, stream));
-  MVG_TRY(mvg_offsets_dlt(ws.mlp_out, 16, ws.ref2d, ws.selected, cams, c.batch, c.views, c.queries, c.joints, c.img_w,
+                         ws.selected, ws.counts, ws.info, ws.ids, ws.ids + B * c.queries, ws.ids + 2 * B * c.queries,
+                         ws.ids + 3 * B * c.queries, stream));
+  MVG_TRY(mvg_offset_chain(ws.attn, ws.info, ws.ids + 2 * B * c.queries, ws.ids + 3 * B * c.queries, w.w_m1, w.b_m1,
+                           w.w_m2, w.b_m2, w.w_m3, w.b_m3, c.batch, c.views, c.queries, c.joints, ws.mlp_out, 4, stream));
+  MVG_TRY(mvg_offsets_dlt(ws.mlp_out, 4, ws.ref2d, ws.selected, cams, c.batch, c.views, c.queries, c.joints, c.img_w,
                           c.img_h, ref_out, refined_out, projs_out, stream));
   if (count_out != nullptr) {
     cudaError_t e = cudaMemcpyAsync(count_out, ws.info, sizeof(int32_t), cudaMemcpyDeviceToDevice,

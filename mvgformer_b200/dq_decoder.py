@@ -210,7 +210,10 @@ class DQDecoderLayer(nn.Module):
             nl = len(self.pose_embed.MLP.layers)
             for i, lyr in enumerate(self.pose_embed.MLP.layers):
                 w, b = lyr.weight.detach(), lyr.bias.detach()
-                if i == nl - 1:                      # pad the 3-row head to a 16-row MMA tile
+                if i == nl - 1:
+                    # fp32 head of the fused chain (the tensor-core path sees its bf16 rounding) ...
+                    pk["head"] = (f32(bf(w).float()), f32(b))
+                    # ... and its 16-row zero-padded MMA tile for the unfused path
                     wp = torch.zeros(16, w.shape[1], dtype=w.dtype, device=w.device)
                     bp = torch.zeros(16, dtype=b.dtype, device=b.device)
                     wp[:3], bp[:3] = w, b
@@ -267,6 +270,7 @@ class DQDecoderLayer(nn.Module):
         # 5. class head + query filter (integer path)
         with prof.stage("class_head"):
             prob = ops.class_head(tgt_update, lw["wc"], lw["bc"], Q, J)           # (B,Q,2)
+        ids = None
         if self.filter_query and indices is not None:
             selected = torch.zeros((B, Q), dtype=torch.uint8, device=tgt.device)
             for b, qs in enumerate(indices):
@@ -280,7 +284,7 @@ class DQDecoderLayer(nn.Module):
                     selected[0, 0] = 1
         else:
             method = "threshold" if self.filter_query else "all"
-            selected, _, info = ops.select_pad(prob, threshold, method, min_one=shard is None)
+            selected, _, info, ids = ops.select_pad(prob, threshold, method, with_ids=True, min_one=shard is None)
             if shard is not None:
                 # (rank, world, group, force): the "always one query" rule (:620-623) is global.
                 # No per-layer collective: the local count is returned and checked after the
@@ -289,14 +293,21 @@ class DQDecoderLayer(nn.Module):
                 self._shard_count = info[0:1]
                 if len(shard) > 3 and shard[3] and shard[0] == 0:
                     selected[0, 0] = 1
+                    ids = None                       # the id arrays no longer describe `selected`
         # 6. offset_net MLP per view
         with prof.stage("offset_mlp"):
-            h = attn
-            nl = len(lw["mlp"])
-            for i, (w, b) in enumerate(lw["mlp"]):
-                last = i == nl - 1
-                h = linear(h, w, b, relu=not last, out_dtype=torch.float32 if last else torch.bfloat16)
-            mlp_out = h.view(B * V * N, -1)
+            if ids is not None and len(lw["mlp"]) == 3 and _use_ffn_chain():
+                # one fused kernel over the rows of the selected queries (csrc/offset_chain.cu)
+                (w1, b1), (w2, b2) = lw["mlp"][0], lw["mlp"][1]
+                mlp_out = ops.offset_chain(attn, info, ids[2], ids[3], w1, b1, w2, b2, lw["head"][0], lw["head"][1],
+                                           Q, J)
+            else:
+                h = attn
+                nl = len(lw["mlp"])
+                for i, (w, b) in enumerate(lw["mlp"]):
+                    last = i == nl - 1
+                    h = linear(h, w, b, relu=not last, out_dtype=torch.float32 if last else torch.bfloat16)
+                mlp_out = h.view(B * V * N, -1)
         # 7. offsets -> undistort -> DLT -> scatter
         with prof.stage("offsets_dlt"):
             new_ref, refined_abs, projs_abs = ops.offsets_dlt(mlp_out, ref2d, selected, ctx.cams,
@@ -340,16 +351,25 @@ class DQDecoder(nn.Module):
         gs, gc = self.grid_size.to(device), self.grid_center.to(device)
         return norm_coords * gs + gc - gs / 2.0
 
+    def prepare(self, src_views, meta, batch_size: int) -> DecoderContext:
+        """The query-independent part of a call (see `forward(ctx=...)`)."""
+        return DecoderContext(src_views, meta, self.layers[0].img_size, list(self.layers), batch_size)
+
     def forward(self, tgt, reference_points, src_views, meta, src_spatial_shapes,
                 src_level_start_index, src_valid_ratios, query_pos=None, src_padding_mask=None,
                 rgb_views=None, output_dir='./', frame_id=None, indices=None, threshold=0.5,
-                indices_all=None, shard=None):
-        """dq_decoder.py:1107-1172.  Extension: `shard=(rank, world, group[, forced_layers])` runs
+                indices_all=None, shard=None, ctx=None):
+        """dq_decoder.py:1107-1172.  Extensions: `shard=(rank, world, group[, forced_layers])` runs
         this rank's contiguous query block (tgt / reference_points / query_pos already sliced
-        with sharding.shard_points); sharding.sharded_decoder_forward gathers the poses."""
+        with sharding.shard_points); sharding.sharded_decoder_forward gathers the poses.
+        `ctx` = a DecoderContext prepared earlier with `self.prepare(src_views, meta, batch)` (the
+        per-frame pyramid work - channels-last hand-off, camera packing, value / offset-map GEMM -
+        does not depend on the queries, so a serving loop can run it for frame i+1 while the layers
+        of frame i execute); src_views / meta are then ignored."""
         if not tgt.is_cuda:
             raise RuntimeError("Not implemented on the CPU")
-        ctx = DecoderContext(src_views, meta, self.layers[0].img_size, list(self.layers), tgt.shape[0])
+        if ctx is None:
+            ctx = self.prepare(src_views, meta, tgt.shape[0])
         output = tgt
         inter, inter_ref, inter_2d, inter_proj, classes = [], [], [], [], []
         ref_points_2d = None

@@ -97,7 +97,7 @@ def gather_results(poses: torch.Tensor, prob: torch.Tensor, counts: torch.Tensor
 
 def sharded_decoder_forward(decoder, tgt, reference_points, src_views, meta, spatial_shapes,
                             level_start_index, query_pos, *, threshold, num_queries, joints, rank,
-                            world, group=None, check: bool = True):
+                            world, group=None, check: bool = True, ctx=None):
     """Runs `decoder` (a DQDecoder with return_intermediate=True) on this rank's query block and
     returns the gathered (poses (B,Q*J,3), class prob (B,Q,2)) of the LAST layer, identical on
     every rank and bit-identical to the unsharded decoder.  `check=False` skips the (host-
@@ -105,7 +105,8 @@ def sharded_decoder_forward(decoder, tgt, reference_points, src_views, meta, spa
     def run(forced):
         hs, refs, r2d, p2d, cls = decoder(tgt, reference_points, src_views, meta, spatial_shapes,
                                           level_start_index, None, query_pos=query_pos,
-                                          threshold=threshold, shard=(rank, world, group, forced))
+                                          threshold=threshold, shard=(rank, world, group, forced),
+                                          **({} if ctx is None else {"ctx": ctx}))
         return gather_results(refs[-1], cls[-1], decoder.last_shard_counts, num_queries, joints,
                               world, group)
     poses, prob, gcounts = run(None)

@@ -799,3 +799,48 @@ def test_query_sharded_blocks_equal_unsharded(world):
     total = torch.stack(counts).sum(0).cpu()
     want = torch.tensor([int((c[..., 1] > thr).sum()) for c in cls], dtype=total.dtype)
     assert torch.equal(total, want) and int(total.min()) > 0
+
+
+# ----------------------------------------------------------------------------- fused offset_net chain
+@pytest.mark.parametrize("B,V,Q,frac", [(1, 5, 1024, 0.5), (2, 3, 40, 1.0), (1, 5, 300, 0.01), (3, 2, 17, 0.3)])
+def test_offset_chain_vs_fp64(B, V, Q, frac):
+    """mvg_offset_chain (offset_net MLP on the selected queries' rows, one tcgen05 kernel) vs the same
+    chain in fp64 torch on the bf16-rounded operands (bf16 rounding left inside: relu(h1) as MMA operand);
+    rows of unselected queries must stay untouched."""
+    J, N = 15, Q * 15
+    rng = np.random.default_rng(Q)
+    f = lambda *sh, sc=1.0: torch.from_numpy((rng.standard_normal(sh) * sc).astype(np.float32))
+    attn = bf16_round(f(B, V, N, 256))
+    w1, w2 = bf16_round(f(256, 256, sc=1 / 16)), bf16_round(f(256, 256, sc=1 / 16))
+    b1, b2 = f(256, sc=0.1), f(256, sc=0.1)
+    w3, b3 = bf16_round(f(3, 256, sc=1 / 16)), f(3, sc=0.1)
+    prob = torch.from_numpy(rng.uniform(0, 1, size=(B, Q, 2)).astype(np.float32))
+    thr = 1.0 - frac
+    sel, counts, info, ids = ops.select_pad(prob.to(DEV), thr, "threshold", with_ids=True)
+    D = lambda t: t.to(DEV)
+    out = ops.offset_chain(D(attn).bfloat16(), info, ids[2], ids[3], D(w1).bfloat16(), D(b1), D(w2).bfloat16(),
+                           D(b2), D(w3), D(b3), Q, J)
+    out.fill_(-7.0)          # ops.offset_chain allocates: call the C entry again on the sentinel-filled buffer
+    from mvgformer_b200 import _lib
+    lib = _lib.load()
+    a_bf, w1_bf, w2_bf = D(attn).bfloat16(), D(w1).bfloat16(), D(w2).bfloat16()
+    b1d, b2d, w3d, b3d = D(b1), D(b2), D(w3), D(b3)
+    _lib.check(lib.mvg_offset_chain(a_bf.data_ptr(), info.data_ptr(), ids[2].data_ptr(), ids[3].data_ptr(),
+                                    w1_bf.data_ptr(), b1d.data_ptr(), w2_bf.data_ptr(), b2d.data_ptr(), w3d.data_ptr(),
+                                    b3d.data_ptr(), B, V, Q, J, out.data_ptr(), 4, _lib.stream_ptr(out.device)),
+               "mvg_offset_chain")
+    torch.cuda.synchronize()
+    out = out.cpu().view(B, V, Q, J, 4)
+    d = lambda t: t.double()
+    h1 = torch.relu(d(attn) @ d(w1).t() + d(b1))
+    h2 = torch.relu(bf16_round(h1.float()).double() @ d(w2).t() + d(b2))
+    ref = (h2 @ d(w3).t() + d(b3)).view(B, V, Q, J, 3)
+    selm = sel.cpu().bool()                                   # (B,Q)
+    assert int(selm.sum()) == int(info[0])
+    got = out[..., :3].permute(0, 2, 1, 3, 4)[selm]           # (n_sel, V, J, 3)
+    want = ref.permute(0, 2, 1, 3, 4)[selm]
+    err = (got.double() - want).abs()
+    assert float(err.max()) < 2e-2 and float(err.mean()) < 1.5e-3, (float(err.max()), float(err.mean()))
+    untouched = out.permute(0, 2, 1, 3, 4)[~selm]
+    assert untouched.numel() == 0 or bool((untouched == -7.0).all())
+    assert bool((out[..., 3].permute(0, 2, 1, 3)[selm] == -7.0).all())      # column 3 is never written
