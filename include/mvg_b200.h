@@ -79,7 +79,8 @@ MVG_API int mvg_pack_cameras(const void* const* fields, const int* dtypes, int b
  *   value (B,S,M,D) dtype `dtype`; spatial_shapes (Lv,2) int64 DEVICE; level_start_index
  *   (Lv) int64 DEVICE; sampling_loc (B,Lq,M,Lv,P,2) and attn_weight (B,Lq,M,Lv,P) dtype
  *   `dtype`; out (B,Lq,M*D) dtype `dtype`, fully overwritten (the reference zero-fills it,
- *   deform_cuda.cu:65).  fp32 accumulation.  D must be 32, M*D <= 1024.
+ *   deform_cuda.cu:65).  dtype MVG_F32 / MVG_BF16 (fp32 accumulation) or MVG_F64 (the reference
+ *   dispatches all floating types, deform_cuda.cu:75).  D must be 32, M*D <= 1024.
  *   `im2col_step` is accepted for signature fidelity; batch % min(batch, step) == 0 is
  *   enforced like deform_cuda.cu:63, the chunk loop itself is not needed.
  */
@@ -266,13 +267,14 @@ MVG_API int mvg_ffn_chain(const void* aver_bf16, const float* tgt, const void* w
 /* Fused offset_net MLP (dq_decoder.py:97-111, :659-717; MLP multi_view_pose_transformer.py:81-102) on the
  * rows of the SELECTED queries only (the reference gathers them into a padded rectangle, :899-932):
  *   out[row, 0..2] = relu(relu(attn[row] @ W1^T + b1) @ W2^T + b2) @ W3^T + b3
- * attn (B*V*N, 256) bf16 (output_proj result); info[0] = number of selected queries and
- * batch_ids / query_ids = their frame / query ids (device; mvg_select_pad's info and *_rev arrays);
+ * attn (B*V*N, 256) bf16 (output_proj result); info, query_ids_pad (= query_ids), batch_ids_rev,
+ * query_ids_rev: the DEVICE outputs of mvg_select_pad (selected query s sits in frame
+ * batch_ids_rev[s] at position query_ids_rev[s] of the padded rectangle, :941-947);
  * W1, W2 (256,256) bf16, b1, b2 (256) fp32, W3 (3,256) fp32, b3 (3) fp32; out (B*V*N, out_ld) fp32:
  * columns 0..2 of the rows of selected queries (all views, all joints) are written, nothing else.
  * One tcgen05 kernel, hidden activations stay on chip, no host synchronisation. */
-MVG_API int mvg_offset_chain(const void* attn_bf16, const int32_t* info, const int64_t* batch_ids,
-                     const int64_t* query_ids, const void* w1, const float* b1, const void* w2,
+MVG_API int mvg_offset_chain(const void* attn_bf16, const int32_t* info, const int64_t* query_ids_pad,
+                     const int64_t* batch_ids_rev, const int64_t* query_ids_rev, const void* w1, const float* b1, const void* w2,
                      const float* b2, const float* w3, const float* b3, int batch, int views, int queries,
                      int joints, float* out, int out_ld, void* stream);
 

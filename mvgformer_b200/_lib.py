@@ -82,7 +82,7 @@ SIGNATURES = {
     "mvg_decoder": [C.POINTER(MvgDecoderConfig), C.POINTER(MvgLayerWeights), _P, _P, _P, _I, _P, _P, _P, _P, _P,
                     _P, _P, _P, _P, _P, _P, _P, _L, _P],
     "mvg_allgather_poses": [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
-    "mvg_offset_chain": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P],
+    "mvg_offset_chain": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P],
     "mvg_nearby_joints_nms": [_P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P],
 }
 

@@ -111,7 +111,8 @@ static int run_layer(const MvgDecoderConfig& c, const MvgSampleParams& prm, cons
   MVG_TRY(mvg_select_pad(prob_out, c.batch, c.queries, c.threshold, c.filter_query ? 0 : 1, c.local_min_one,
                          ws.selected, ws.counts, ws.info, ws.ids, ws.ids + B * c.queries, ws.ids + 2 * B * c.queries,
                          ws.ids + 3 * B * c.queries, stream));
-  MVG_TRY(mvg_offset_chain(ws.attn, ws.info, ws.ids + 2 * B * c.queries, ws.ids + 3 * B * c.queries, w.w_m1, w.b_m1,
+  MVG_TRY(mvg_offset_chain(ws.attn, ws.info, ws.ids + B * c.queries, ws.ids + 2 * B * c.queries,
+                           ws.ids + 3 * B * c.queries, w.w_m1, w.b_m1,
                            w.w_m2, w.b_m2, w.w_m3, w.b_m3, c.batch, c.views, c.queries, c.joints, ws.mlp_out, 4, stream));
   MVG_TRY(mvg_offsets_dlt(ws.mlp_out, 4, ws.ref2d, ws.selected, cams, c.batch, c.views, c.queries, c.joints, c.img_w,
                           c.img_h, ref_out, refined_out, projs_out, stream));

@@ -124,6 +124,48 @@ deform_forward_kernel(const T* __restrict__ value, const int64_t* __restrict__ s
   Vec16<T>::store(out + gid * D + sub * E, acc);
 }
 
+// float64 (the reference dispatches AT_DISPATCH_FLOATING_TYPES, deform_cuda.cu:75): used for gradient
+// checks only, so this is the plain formulation - one lane per (b, q, head, channel), a warp = the 32
+// channels of one head (128-byte coalesced corner reads), double arithmetic in the reference's order
+// (deform_im2col_cuda.cuh:247-309, :41-93).
+__global__ void __launch_bounds__(256)
+deform_forward_f64_kernel(const double* __restrict__ value, const int64_t* __restrict__ shapes,
+                          const int64_t* __restrict__ lsi, const double* __restrict__ loc_all,
+                          const double* __restrict__ attn_all, int64_t n, int spatial_size, int num_heads,
+                          int num_levels, int num_query, int num_point, double* __restrict__ out) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int c = static_cast<int>(idx % 32);
+  const int64_t g = idx / 32;                              // (b, q, m)
+  const int m = static_cast<int>(g % num_heads);
+  const int64_t b = g / (static_cast<int64_t>(num_heads) * num_query);
+  const double* loc = loc_all + g * num_levels * num_point * 2;
+  const double* attn = attn_all + g * num_levels * num_point;
+  const double* vb = value + b * spatial_size * num_heads * 32;
+  double acc = 0.0;
+  for (int l = 0; l < num_levels; ++l) {
+    const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
+    const double* vl = vb + lsi[l] * num_heads * 32 + m * 32 + c;
+    for (int p = 0; p < num_point; ++p) {
+      const double loc_w = loc[(l * num_point + p) * 2], loc_h = loc[(l * num_point + p) * 2 + 1];
+      const double wgt = attn[l * num_point + p];
+      const double h_im = loc_h * H - 0.5, w_im = loc_w * W - 0.5;
+      if (h_im > -1 && w_im > -1 && h_im < H && w_im < W) {
+        const int h_low = static_cast<int>(floor(h_im)), w_low = static_cast<int>(floor(w_im));
+        const double lh = h_im - h_low, lw = w_im - w_low, hh = 1 - lh, hw = 1 - lw;
+        const int64_t rs = static_cast<int64_t>(num_heads) * 32;
+        double v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+        if (h_low >= 0 && w_low >= 0) v1 = vl[(static_cast<int64_t>(h_low) * W + w_low) * rs];
+        if (h_low >= 0 && w_low + 1 <= W - 1) v2 = vl[(static_cast<int64_t>(h_low) * W + w_low + 1) * rs];
+        if (h_low + 1 <= H - 1 && w_low >= 0) v3 = vl[(static_cast<int64_t>(h_low + 1) * W + w_low) * rs];
+        if (h_low + 1 <= H - 1 && w_low + 1 <= W - 1) v4 = vl[(static_cast<int64_t>(h_low + 1) * W + w_low + 1) * rs];
+        acc += (hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4) * wgt;
+      }
+    }
+  }
+  out[idx] = acc;
+}
+
 }  // namespace mvg
 
 extern "C" int mvg_deform_forward(const void* value, const int64_t* spatial_shapes,
@@ -160,6 +202,12 @@ extern "C" int mvg_deform_forward(const void* value, const int64_t* spatial_shap
         static_cast<const __nv_bfloat16*>(sampling_loc),
         static_cast<const __nv_bfloat16*>(attn_weight), n_groups, spatial_size, num_heads,
         num_levels, num_query, num_point, static_cast<__nv_bfloat16*>(out));
+  } else if (dtype == MVG_F64) {
+    const int64_t n = n_groups * 32;
+    deform_forward_f64_kernel<<<static_cast<unsigned>((n + threads - 1) / threads), threads, 0, st>>>(
+        static_cast<const double*>(value), spatial_shapes, level_start_index,
+        static_cast<const double*>(sampling_loc), static_cast<const double*>(attn_weight), n, spatial_size,
+        num_heads, num_levels, num_query, num_point, static_cast<double*>(out));
   } else {
     set_error("mvg_deform_forward: unsupported dtype %d", dtype);
     return MVG_EUNSUPPORTED;

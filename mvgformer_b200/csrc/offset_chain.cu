@@ -8,7 +8,7 @@
 // The reference runs the MLP on the SELECTED queries only (it gathers them into a padded
 // rectangle first, dq_decoder.py:899-932).  Here the 128-row A tile of the first GEMM is gathered
 // straight from the rows of the selected queries (all views, all joints) by the epilogue warps
-// - the batch / query ids come from mvg_select_pad, the row count lives on the device, so there is
+// - the id arrays come from mvg_select_pad, the row count lives on the device, so there is
 // no host synchronisation - and (dx, dy, confidence logit) are scattered back to the rows'
 // natural positions; rows of unselected queries are never read (mvg_offsets_dlt ignores them).
 // Before: three full-size GEMMs (76 800 rows, 0.24 ms per step at Q = 1024) with two bf16 round
@@ -32,9 +32,10 @@ static_assert(kOcSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm
 
 struct OffsetChainParams {
   const __nv_bfloat16* attn;     // (B*V*N, 256) bf16
-  const int32_t* info;           // [0] = number of selected queries (device)
-  const int64_t* batch_ids;      // (n_sel) frame of the s-th selected query   (mvg_select_pad *_rev arrays)
-  const int64_t* query_ids;      // (n_sel) its query id
+  const int32_t* info;           // [0] = number of selected queries, [1] = padded queries per frame (device)
+  const int64_t* query_ids_pad;  // (B * info[1]) query ids of the padded rectangle   (mvg_select_pad outputs)
+  const int64_t* batch_ids_rev;  // (n_sel) frame of the s-th selected query
+  const int64_t* query_ids_rev;  // (n_sel) its position inside the frame's padded row
   const float* b1;               // (256)
   const float* b2;               // (256)
   const float* w3;               // (3, 256) fp32
@@ -64,7 +65,9 @@ __device__ __forceinline__ int64_t oc_row_of(int64_t a, int64_t n_active, const 
   const int64_t s = a / vj;
   const int rem = static_cast<int>(a - s * vj);
   const int v = rem / p.joints, j = rem - v * p.joints;
-  const int64_t b = __ldg(p.batch_ids + s), q = __ldg(p.query_ids + s);
+  // dq_decoder.py:941-947: valid entry s of the padded (B, max_count) rectangle
+  const int64_t b = __ldg(p.batch_ids_rev + s), pos = __ldg(p.query_ids_rev + s);
+  const int64_t q = __ldg(p.query_ids_pad + b * __ldg(p.info + 1) + pos);
   return (b * p.views + v) * p.points + q * p.joints + j;
 }
 
@@ -273,12 +276,12 @@ offset_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
 
 }  // namespace mvg
 
-extern "C" int mvg_offset_chain(const void* attn_bf16, const int32_t* info, const int64_t* batch_ids,
-                                const int64_t* query_ids, const void* w1, const float* b1, const void* w2,
+extern "C" int mvg_offset_chain(const void* attn_bf16, const int32_t* info, const int64_t* query_ids_pad,
+                                const int64_t* batch_ids_rev, const int64_t* query_ids_rev, const void* w1, const float* b1, const void* w2,
                                 const float* b2, const float* w3, const float* b3, int batch, int views, int queries,
                                 int joints, float* out, int out_ld, void* stream) {
   using namespace mvg;
-  MVG_REQUIRE(attn_bf16 && info && batch_ids && query_ids && w1 && b1 && w2 && b2 && w3 && b3 && out,
+  MVG_REQUIRE(attn_bf16 && info && query_ids_pad && batch_ids_rev && query_ids_rev && w1 && b1 && w2 && b2 && w3 && b3 && out,
               "mvg_offset_chain: null pointer");
   MVG_REQUIRE(batch > 0 && views > 0 && queries > 0 && joints > 0 && out_ld >= 3, "mvg_offset_chain: bad shape");
   const void* ptrs[] = {attn_bf16, w1, b1, w2, b2, w3};
@@ -300,7 +303,8 @@ extern "C" int mvg_offset_chain(const void* attn_bf16, const int32_t* info, cons
     }
     attr_set = true;
   }
-  OffsetChainParams p{static_cast<const __nv_bfloat16*>(attn_bf16), info, batch_ids, query_ids, b1, b2, w3, b3, out,
+  OffsetChainParams p{static_cast<const __nv_bfloat16*>(attn_bf16), info, query_ids_pad, batch_ids_rev, query_ids_rev, b1, b2, w3,
+                      b3, out,
                       out_ld, views, joints, queries * joints};
   const int64_t max_tiles = (rows + kBlockM - 1) / kBlockM;
   const int grid = static_cast<int>(max_tiles < kNumSMs ? max_tiles : kNumSMs);

@@ -1,4 +1,8 @@
-// 2D offsets -> refined 2D points -> DLT triangulation, one thread per (frame, query, joint).
+// 2D offsets -> refined 2D points -> DLT triangulation, FOUR lanes per (frame, query, joint): the lanes
+// split the views (view softmax, inverse affine, 5-iteration undistort, the two DLT rows per view),
+// the 4x4 normal matrices are summed with warp shuffles, every lane then runs the same Jacobi
+// eigen-solve (no exchange needed) and lane 0 stores.  One thread per problem left 94 % of the warp
+// slots idle (15 360 problems on 148 SMs) with every view's ~400-cycle division chain in series.
 //
 //   a9  calculate_2d_offsets tail   lib/models/dq_decoder.py:678-707
 //   a10 inverse affine + undistort   lib/models/dq_decoder.py:413-422, :119-204, P: :223-246
@@ -21,7 +25,7 @@
 
 namespace mvg {
 
-constexpr int kJacobiSweeps = 6;   // 1e-9 mm vs fp64 SVD already at 6 (numpy prototype)
+constexpr int kJacobiSweeps = 8;   // upper bound; the graded stopping test usually ends after 4-5 sweeps
 
 // Smallest-eigenvalue eigenvector of the symmetric 4x4 `H` (upper triangle used).
 __device__ __forceinline__ void smallest_eigvec4(double H[4][4], double out[4]) {
@@ -35,6 +39,15 @@ __device__ __forceinline__ void smallest_eigvec4(double H[4][4], double out[4]) 
   constexpr int kPairs[6][2] = {{0, 1}, {2, 3}, {0, 2}, {1, 3}, {0, 3}, {1, 2}};
 #pragma unroll 1
   for (int sweep = 0; sweep < kJacobiSweeps; ++sweep) {
+    // graded stopping test |a_pq| <= eps sqrt(a_pp a_qq) for all pairs (the matrix spans 12 orders
+    // of magnitude, a norm-wise test would stop too early for the small eigenvalue)
+    bool done = true;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      const int p = kPairs[e][0], q = kPairs[e][1];
+      done = done && (H[p][q] * H[p][q] <= 1e-32 * fabs(H[p][p] * H[q][q]));
+    }
+    if (done) break;
 #pragma unroll
     for (int round = 0; round < 3; ++round) {
       double cs[2], sn[2], tt[2];
@@ -120,6 +133,8 @@ __device__ __forceinline__ void solve_and_store(double H[4][4], float* out3) {
   out3[2] = static_cast<float>(x[2] / x[3]);
 }
 
+constexpr int kDltLanes = 4;       // lanes per (frame, query, joint) problem
+
 __global__ void __launch_bounds__(128)
 offsets_dlt_kernel(const float* __restrict__ mlp_out, int mlp_ld, const float* __restrict__ ref2d,
                    const uint8_t* __restrict__ selected, const MvgCamera* __restrict__ cams,
@@ -127,15 +142,19 @@ offsets_dlt_kernel(const float* __restrict__ mlp_out, int mlp_ld, const float* _
                    float* __restrict__ new_ref, float* __restrict__ refined_abs,
                    float* __restrict__ projs_abs) {
   const int64_t N = static_cast<int64_t>(Q) * J;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<int64_t>(B) * N) return;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t idx = gid / kDltLanes;                   // problem
+  const int sl = static_cast<int>(gid % kDltLanes);      // this lane's first view
+  if (idx >= static_cast<int64_t>(B) * N) return;        // whole 4-lane groups leave together
+  // shuffles stay inside the 4-lane group; all of its lanes are alive here
+  const uint32_t gmask = 0xfu << ((threadIdx.x & 31) & ~3);
   const int b = static_cast<int>(idx / N);
   const int64_t n = idx % N;
   const int q = static_cast<int>(n / J);
   float* oref = new_ref + idx * 3;
   if (!selected[static_cast<int64_t>(b) * Q + q]) {       // dq_decoder.py:1013-1029
-    oref[0] = 0.f; oref[1] = 0.f; oref[2] = 0.f;
-    for (int v = 0; v < V; ++v) {
+    if (sl == 0) { oref[0] = 0.f; oref[1] = 0.f; oref[2] = 0.f; }
+    for (int v = sl; v < V; v += kDltLanes) {
       const int64_t o = ((static_cast<int64_t>(b) * V + v) * N + n) * 2;
       refined_abs[o] = 0.f; refined_abs[o + 1] = 0.f;
       projs_abs[o] = 0.f; projs_abs[o + 1] = 0.f;
@@ -144,11 +163,15 @@ offsets_dlt_kernel(const float* __restrict__ mlp_out, int mlp_ld, const float* _
   }
   // confidence = softmax over views of the logits (nn.Softmax(dim=0), :305,:706-707)
   float mx = -INFINITY;
-  for (int v = 0; v < V; ++v)
+  for (int v = sl; v < V; v += kDltLanes)
     mx = fmaxf(mx, __ldg(mlp_out + ((static_cast<int64_t>(b) * V + v) * N + n) * mlp_ld + 2));
+  mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, 2));
   float den = 0.f;
-  for (int v = 0; v < V; ++v)
+  for (int v = sl; v < V; v += kDltLanes)
     den += expf(__ldg(mlp_out + ((static_cast<int64_t>(b) * V + v) * N + n) * mlp_ld + 2) - mx);
+  den += __shfl_xor_sync(gmask, den, 1);
+  den += __shfl_xor_sync(gmask, den, 2);
 
   double H[4][4];
 #pragma unroll
@@ -156,7 +179,7 @@ offsets_dlt_kernel(const float* __restrict__ mlp_out, int mlp_ld, const float* _
 #pragma unroll
     for (int c = 0; c < 4; ++c) H[a][c] = 0.0;
 
-  for (int v = 0; v < V; ++v) {
+  for (int v = sl; v < V; v += kDltLanes) {
     const int64_t row = (static_cast<int64_t>(b) * V + v) * N + n;
     const MvgCamera* cam = cams + static_cast<int64_t>(b) * V + v;
     const float ox = __ldg(mlp_out + row * mlp_ld), oy = __ldg(mlp_out + row * mlp_ld + 1);
@@ -194,7 +217,19 @@ offsets_dlt_kernel(const float* __restrict__ mlp_out, int mlp_ld, const float* _
     const float w = fadd(fmul(cam->f[1], y), cam->c[1]);
     accumulate_rows(cam->P, u, w, conf, H);
   }
-  solve_and_store(H, oref);
+  // normal equations of all views: butterfly over the group's 4 lanes (upper triangle, fp64)
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = a; c < 4; ++c) {
+      double h = H[a][c];
+      h += __shfl_xor_sync(gmask, h, 1);
+      h += __shfl_xor_sync(gmask, h, 2);
+      H[a][c] = h;
+    }
+  float o3[3];
+  solve_and_store(H, o3);                                 // identical on the 4 lanes
+  if (sl == 0) { oref[0] = o3[0]; oref[1] = o3[1]; oref[2] = o3[2]; }
 }
 
 __global__ void __launch_bounds__(128)
@@ -231,7 +266,7 @@ extern "C" int mvg_offsets_dlt(const float* mlp_out, int mlp_ld, const float* re
               "mvg_offsets_dlt: null pointer");
   MVG_REQUIRE(batch > 0 && views > 0 && queries > 0 && joints > 0, "mvg_offsets_dlt: empty shape");
   MVG_REQUIRE(mlp_ld >= 3, "mvg_offsets_dlt: mlp_ld %d < 3", mlp_ld);
-  const int64_t total = static_cast<int64_t>(batch) * queries * joints;
+  const int64_t total = static_cast<int64_t>(batch) * queries * joints * kDltLanes;
   const int threads = 128;
   offsets_dlt_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0,
                        static_cast<cudaStream_t>(stream)>>>(

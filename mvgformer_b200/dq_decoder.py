@@ -299,8 +299,7 @@ class DQDecoderLayer(nn.Module):
             if ids is not None and len(lw["mlp"]) == 3 and _use_ffn_chain():
                 # one fused kernel over the rows of the selected queries (csrc/offset_chain.cu)
                 (w1, b1), (w2, b2) = lw["mlp"][0], lw["mlp"][1]
-                mlp_out = ops.offset_chain(attn, info, ids[2], ids[3], w1, b1, w2, b2, lw["head"][0], lw["head"][1],
-                                           Q, J)
+                mlp_out = ops.offset_chain(attn, info, ids, w1, b1, w2, b2, lw["head"][0], lw["head"][1], Q, J)
             else:
                 h = attn
                 nl = len(lw["mlp"])

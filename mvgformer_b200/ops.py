@@ -259,16 +259,17 @@ def ffn_chain(aver: torch.Tensor, tgt: torch.Tensor, w_fu, b_fu, g2, e2, eps2, w
     return out
 
 
-def offset_chain(attn: torch.Tensor, info: torch.Tensor, batch_ids: torch.Tensor, query_ids: torch.Tensor,
-                 w1, b1, w2, b2, w3, b3, queries: int, joints: int) -> torch.Tensor:
+def offset_chain(attn: torch.Tensor, info: torch.Tensor, ids, w1, b1, w2, b2, w3, b3, queries: int,
+                 joints: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fused offset_net MLP on the rows of the selected queries.  attn (B,V,N,256) bf16;
-    info / batch_ids / query_ids from select_pad(with_ids=True) -> mlp_out (B*V*N, 4) fp32 (columns
-    0..2 of the selected queries' rows written, the rest untouched)."""
+    info / ids = select_pad(with_ids=True) outputs -> mlp_out (B*V*N, 4) fp32 (columns 0..2 of the
+    selected queries' rows written, the rest untouched)."""
     lib = _lib.load()
     B, V, N, _ = attn.shape
-    out = torch.empty((B * V * N, 4), dtype=torch.float32, device=attn.device)
-    check(lib.mvg_offset_chain(attn.data_ptr(), info.data_ptr(), batch_ids.data_ptr(), query_ids.data_ptr(),
-                               w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), w3.data_ptr(),
-                               b3.data_ptr(), B, V, queries, joints, out.data_ptr(), 4, stream_ptr(attn.device)),
-          "mvg_offset_chain")
+    if out is None:
+        out = torch.empty((B * V * N, 4), dtype=torch.float32, device=attn.device)
+    check(lib.mvg_offset_chain(attn.data_ptr(), info.data_ptr(), ids[1].data_ptr(), ids[2].data_ptr(),
+                               ids[3].data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                               w3.data_ptr(), b3.data_ptr(), B, V, queries, joints, out.data_ptr(),
+                               int(out.stride(0)), stream_ptr(attn.device)), "mvg_offset_chain")
     return out

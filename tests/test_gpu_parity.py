@@ -818,17 +818,9 @@ def test_offset_chain_vs_fp64(B, V, Q, frac):
     thr = 1.0 - frac
     sel, counts, info, ids = ops.select_pad(prob.to(DEV), thr, "threshold", with_ids=True)
     D = lambda t: t.to(DEV)
-    out = ops.offset_chain(D(attn).bfloat16(), info, ids[2], ids[3], D(w1).bfloat16(), D(b1), D(w2).bfloat16(),
-                           D(b2), D(w3), D(b3), Q, J)
-    out.fill_(-7.0)          # ops.offset_chain allocates: call the C entry again on the sentinel-filled buffer
-    from mvgformer_b200 import _lib
-    lib = _lib.load()
-    a_bf, w1_bf, w2_bf = D(attn).bfloat16(), D(w1).bfloat16(), D(w2).bfloat16()
-    b1d, b2d, w3d, b3d = D(b1), D(b2), D(w3), D(b3)
-    _lib.check(lib.mvg_offset_chain(a_bf.data_ptr(), info.data_ptr(), ids[2].data_ptr(), ids[3].data_ptr(),
-                                    w1_bf.data_ptr(), b1d.data_ptr(), w2_bf.data_ptr(), b2d.data_ptr(), w3d.data_ptr(),
-                                    b3d.data_ptr(), B, V, Q, J, out.data_ptr(), 4, _lib.stream_ptr(out.device)),
-               "mvg_offset_chain")
+    out = torch.full((B * V * N, 4), -7.0, dtype=torch.float32, device=DEV)     # sentinel: untouched rows
+    ops.offset_chain(D(attn).bfloat16(), info, ids, D(w1).bfloat16(), D(b1), D(w2).bfloat16(), D(b2), D(w3), D(b3),
+                     Q, J, out=out)
     torch.cuda.synchronize()
     out = out.cpu().view(B, V, Q, J, 4)
     d = lambda t: t.double()
@@ -844,3 +836,13 @@ def test_offset_chain_vs_fp64(B, V, Q, frac):
     untouched = out.permute(0, 2, 1, 3, 4)[~selm]
     assert untouched.numel() == 0 or bool((untouched == -7.0).all())
     assert bool((out[..., 3].permute(0, 2, 1, 3)[selm] == -7.0).all())      # column 3 is never written
+
+
+def test_deform_forward_fp64():
+    """float64 dispatch of the op (the reference: AT_DISPATCH_FLOATING_TYPES, deform_cuda.cu:75)."""
+    value, sh, lsi, loc, attn = deform_inputs(9, B=2, Lq=41)
+    v, l, a = value.double(), loc.double(), attn.double()
+    ref = orc.deform_core(v, sh, lsi, l, a)
+    out = mvg.deform_forward(v.to(DEV), sh.to(DEV), lsi.to(DEV), l.to(DEV), a.to(DEV), 64)
+    assert out.dtype == torch.float64 and out.shape == ref.shape
+    assert torch.allclose(out.cpu(), ref, atol=1e-12, rtol=1e-12)
