@@ -631,6 +631,11 @@ def run_ours(a):
         import parity_tools as pt
         sc32 = syn.make_scene(batch=B, n_views=V, num_instance=Q, seed=0)
         parity = pt.summarize(pt.decoder_parity_report(sc32, sd, L, a.threshold))
+        # the same scene with the weight preset whose 2D refinements are ~1 px (the views agree on a joint,
+        # as a trained network's do) - the regime the north star's 0.1 mm refers to
+        sd1 = syn.make_decoder_state_dict(L, np.random.default_rng(1), offset_px=1.0)
+        parity["offsets_1px_preset"] = pt.summarize(pt.decoder_parity_report(sc32, sd1, L, a.threshold))
+        parity["weights"] = "the timed step's weights: random 2D offsets of ~6 px per view (stress preset)"
         parity["note"] = ("same scene and weights as the timed step (features / GEMM weights rounded to bf16 for both "
                           "sides); mm = per-joint 3D distance; well_conditioned = DLT systems with sigma4/sigma3 < 0.5 "
                           "(the others move by metres per 0.005 px in exact arithmetic); fp32 oracle = the reference's "

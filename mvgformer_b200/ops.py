@@ -150,7 +150,8 @@ def select_pad(prob: torch.Tensor, threshold: float, method: str = "threshold",
     info = torch.empty((4,), dtype=torch.int32, device=dev)
     ids: List[Optional[torch.Tensor]] = [None] * 4
     if with_ids:
-        ids = [torch.zeros((B * Q,), dtype=torch.int64, device=dev) for _ in range(4)]
+        # only the first B*max_count / n_valid entries are defined (written by the kernel)
+        ids = [torch.empty((B * Q,), dtype=torch.int64, device=dev) for _ in range(4)]
     code = {"threshold": 0, "all": 1}[method]
     check(lib.mvg_select_pad(prob.data_ptr(), B, Q, float(threshold), code, 1 if min_one else 0,
                              selected.data_ptr(),

@@ -24,8 +24,8 @@ for n, t in step:
 mvg_t = sum(t for n, t in step if "mvg::" in n)
 with open(os.path.join(P, f"launches_{tag}_summary.txt"), "w") as f:
     f.write(f"ncu launch list of ONE eager decoder step (bench.py --no-graph), B=1 V=5 Q=1024 L=4, B200\n"
-            f"command: ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 400 --csv python bench.py "
-            f"--steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-graph   (tools/profile_round.sh)\n"
+            f"command: ncu --metrics gpu__time_duration.sum --clock-control none -s <skip> -c 400 --csv python bench.py "
+            f"--steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-graph --batch8 0   (tools/profile_round.sh)\n"
             f"(per-launch times are cold-cache and serialised: compare SHARES, not absolutes)\n\n"
             f" count    total_us   share  kernel\n")
     for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
@@ -64,20 +64,26 @@ def val(r, name):
     return v
 traffic = None
 with open(os.path.join(P, f"ncu_kernels_{tag}.txt"), "w") as f:
-    f.write("ncu --set full --clock-control none, the 15 libmvg_b200 launches of one decoder layer (+ pyramid hand-off and\n"
-            "value GEMM of the call) in an eager step (bench.py --no-graph), B200 (tools/profile_round.sh)\n"
+    f.write("ncu --set full --clock-control none, the libmvg_b200 launches of one decoder layer (+ camera packing, pyramid\n"
+            "hand-off and value GEMM of the call) in an eager step (bench.py --no-graph), B200 (tools/profile_round.sh)\n"
             "columns: " + ", ".join(c for c, _ in cols) + "\n\n")
     for r in rr[2:]:
         name = re.sub(r"\(.*", "", r[hx["Kernel Name"]]).replace("void ", "")
         f.write(name + "\n   " + "  ".join(f"{c}={val(r, m):.4g}" for c, m in cols) + "\n")
-        if "gather_kernel" in name:
-            traffic = dict(dram_read_bytes=int(val(r, "dram__bytes_read.sum") * 1e6),
-                           dram_write_bytes=int(val(r, "dram__bytes_write.sum") * 1e6))
+        if any(k in name for k in ("gather_kernel", "project_bin", "bin_scan", "bin_scatter", "sample_params",
+                                   "gather_tiles", "gather_direct")):
+            # the gather STAGE = every kernel mvg_project_sample_fused launches (first layer in the capture)
+            traffic = traffic or dict(dram_read_bytes=0, dram_write_bytes=0, kernels=[])
+            if name not in traffic["kernels"]:
+                traffic["kernels"].append(name)
+                traffic["dram_read_bytes"] += int(val(r, "dram__bytes_read.sum") * 1e6)
+                traffic["dram_write_bytes"] += int(val(r, "dram__bytes_write.sum") * 1e6)
 print(open(os.path.join(P, f"ncu_kernels_{tag}.txt")).read())
 if traffic:
     traffic["project_sample_fused_dram_bytes_per_launch"] = traffic["dram_read_bytes"] + traffic["dram_write_bytes"]
     traffic["launches_averaged"] = 1
-    traffic["source"] = f"profiles/ncu_kernels_{tag}.txt (ncu --set full, gather_kernel<3> of layer 0; gpurun_out/step_{tag}.ncu-rep)"
+    traffic["source"] = (f"profiles/ncu_kernels_{tag}.txt (ncu --set full, summed over the kernels of one layer's "
+                         f"mvg_project_sample_fused call; gpurun_out/step_{tag}.ncu-rep)")
     json.dump(traffic, open(os.path.join(P, "roofline_traffic.json"), "w"), indent=1)
     print(traffic)
 shutil.copy(os.path.join(G, f"bench_{tag}.json"), os.path.join(P, f"bench_{tag}.json"))
