@@ -70,55 +70,100 @@ def workload_config(a, world):
 
 # ------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples nvidia-smi while the timed region runs (B200_PROFILING.md clocks line)."""
+    """Samples SM clock + clock-event reasons while the timed region runs (B200_PROFILING.md clocks
+    line): NVML in a thread every ~2 ms (a timed region is tens of milliseconds); `nvidia-smi -lms`
+    as the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []          # (sm MHz, max MHz, set of reasons)
         self.proc = None
+        self.nvml = None
+        self._stop = threading.Event()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                 "-lms", "100", "-i", str(self._physical_index())], stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        nv = self.nvml
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((mhz, self.max_mhz, {n for n, bit in names if mask & bit}))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _read_smi(self):
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 8:
-                self.rows.append(parts)
+                try:
+                    self.rows.append((float(parts[1]), float(parts[2]),
+                                      {n for n, val in zip(("hw_slowdown", "hw_thermal_slowdown",
+                                                            "sw_thermal_slowdown", "sw_power_cap"), parts[4:8])
+                                       if val.lower().startswith("active")}))
+                except ValueError:
+                    continue
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=1)
+            source = "nvml"
+        elif self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                  "sw_power_cap"), r[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            source = "nvidia-smi"
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"]}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = set().union(*[r[2] for r in self.rows]) if self.rows else set()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(r[1] for r in self.rows) if self.rows else None,
+                "reasons": sorted(reasons), "samples": len(sm), "source": source}
 
 
 # ------------------------------------------------------------------------------- CPU arm

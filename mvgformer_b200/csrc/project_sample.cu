@@ -311,8 +311,16 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const GatherWs ws) {
 __device__ __forceinline__ __half2 u32_as_half2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 __device__ __forceinline__ uint32_t half2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
+// Per-warp scratch of sample_params_kernel: the Linear outputs of one item after the `.view` scramble,
+// i.e. per head m its LV*16 flat offsets and LV*8 flat logits.  The head stride is padded to 4 banks
+// (mod 32), so that phase B's lanes (head m = lane & 7, sample group lane >> 3) read conflict-free
+// (the unpadded [level][192] layout cost a 4-way conflict on the offsets and 2-way on the logits).
 template <int LV> struct ParamScratch {
-  float proj[LV][kQP];                    // per pyramid level: Linear outputs (offsets | logits)
+  static constexpr int kOffN = LV * 16, kLogN = LV * 8;
+  static constexpr int kOffStride = kOffN + (36 - kOffN % 32) % 32;
+  static constexpr int kLogStride = kLogN + (36 - kLogN % 32) % 32;
+  float off[kHeads * kOffStride];
+  float logit[kHeads * kLogStride];
 };
 
 __device__ __forceinline__ void fma8_f16(float (&acc)[8], const uint4& c, float w) {
@@ -337,7 +345,8 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
   ParamScratch<LV>* scratch = reinterpret_cast<ParamScratch<LV>*>(smem_dyn);        // [kPWarps]
   __shared__ int s_bb[kHeads][LV][4];     // x0 min, y0 min, x0 max, y0 max
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  ParamScratch<LV>& sc = scratch[warp];
+  using PS = ParamScratch<LV>;
+  PS& sc = scratch[warp];
   const int N = prm.points, V = prm.views, B = prm.batch;
   const int ldg = prm.ld_g;
   constexpr int NS = LV * 8;             // samples per head
@@ -447,9 +456,21 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
           float r8[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
           for (int c = 0; c < 4; ++c) fma8_f16(r8, cn[l & 1][c], cwgt[l & 1][c]);
-          float4* dst = reinterpret_cast<float4*>(&sc.proj[l][lane * 8]);
-          dst[0] = make_float4(r8[0], r8[1], r8[2], r8[3]);
-          dst[1] = make_float4(r8[4], r8[5], r8[6], r8[7]);
+          // flat index after the `.view`: offsets l*128 + 8 lane .. +7, logits l*64 + 8 (lane - 16) .. +7
+          // (8 consecutive flat indices never straddle a head: LV*16 and LV*8 are multiples of 8)
+          float4* dst;
+          if (lane < 16) {
+            const int f0 = l * 128 + lane * 8;
+            dst = reinterpret_cast<float4*>(&sc.off[(f0 / PS::kOffN) * PS::kOffStride + f0 % PS::kOffN]);
+          } else {
+            const int g0 = l * 64 + (lane - 16) * 8;
+            dst = reinterpret_cast<float4*>(&sc.logit[(g0 / PS::kLogN) * PS::kLogStride + g0 % PS::kLogN]);
+          }
+          // lanes 4 apart hit the same banks: they store their two halves in opposite order
+          const int h0 = (lane >> 2) & 1;
+          const float4 lo4 = make_float4(r8[0], r8[1], r8[2], r8[3]), hi4 = make_float4(r8[4], r8[5], r8[6], r8[7]);
+          dst[h0] = h0 ? hi4 : lo4;
+          dst[h0 ^ 1] = h0 ? lo4 : hi4;
         }
       }
       __syncwarp();
@@ -460,8 +481,7 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
         float mx = -INFINITY;
 #pragma unroll
         for (int i = 0; i < NS / 4; ++i) {
-          const int g = m * NS + sub + 4 * i;          // flat logit index after the `.view`
-          lg[i] = sc.proj[g >> 6][128 + (g & 63)];
+          lg[i] = sc.logit[m * PS::kLogStride + sub + 4 * i];      // flat logit m * NS + sub + 4 i after the `.view`
           mx = fmaxf(mx, lg[i]);
         }
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
@@ -494,8 +514,8 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
             const int i = 2 * l + e;                     // sample r = sub + 4 i of this head
             const int r = sub + 4 * i;
             const float wgt = lg[i] * inv_sum;
-            const int f = m * (NS * 2) + 2 * r;          // flat offset index after the `.view`
-            const float2 off = *reinterpret_cast<const float2*>(&sc.proj[f >> 7][f & 127]);
+            // flat offset index after the `.view`: m * (NS * 2) + 2 r
+            const float2 off = *reinterpret_cast<const float2*>(&sc.off[m * PS::kOffStride + 2 * r]);
             const float w_im = bx + off.x, h_im = by + off.y;
             const bool inside = h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW;
             const float fh = floorf(h_im), fw = floorf(w_im);
