@@ -29,11 +29,12 @@
 //                        (warp-aggregated atomics).
 //   bin_scan_kernel      one block: key offsets, and CHUNKS of <= 128 same-key items.
 //   bin_scatter_kernel   counting-sort scatter -> item list ordered by key.
-//   sample_params_kernel one CTA per chunk, one warp per item: phase A samples the pre-projected
-//                        192-channel map G at the reference point (+ qproj), phase B does the
-//                        24-way softmax and, per (head, sample), the clamped 2x2 texel block and
-//                        its four bilinear x attention weights (fp16) -> 16-byte records in the
-//                        workspace, plus the bounding box of every (chunk, head, level)'s samples.
+//   sample_params_kernel work queue over (chunk, 32 items), one warp per item: phase A samples the
+//                        pre-projected 192-channel map G at the reference point (+ qproj), phase B
+//                        does the 24-way softmax and, per (head, sample), the clamped 2x2 texel block
+//                        and its four bilinear x attention weights (fp16) -> 16-byte records in the
+//                        workspace, plus the bounding box of every (chunk, head, level)'s samples
+//                        (atomic min / max into the chunk's boxes).
 //   gather_tiles_kernel  persistent, one CTA per SM: a producer warp stages, per (chunk, head),
 //                        the bounding-box tile of each level (rows of the head-major value
 //                        tensor, one cp.async.bulk per tile row, mbarrier complete_tx) into a
@@ -68,6 +69,8 @@ constexpr int kPWarps = MVG_P_WARPS;   // sample_params: warps per CTA
 constexpr int kGWarps = 16;        // gather_tiles: consumer warps per CTA (+ 1 producer warp)
 constexpr int kScanThreads = 1024;
 constexpr int kIPW = kChunk / kGWarps;   // items per consumer warp and unit
+constexpr int kPart = 32;          // sample_params work item: kPart items of one chunk
+constexpr int kParts = kChunk / kPart;
 constexpr int kRecBytes = 128;     // records of one (item, head, level): 2 block columns x 8 points x 8 B
 
 // per-level shared-memory region capacity in texels (64 B each) for the tiled gather
@@ -84,19 +87,20 @@ struct GatherWs {
   int* counts;        // [BV]            in-view items per (frame, view)       (zeroed per call)
   int* hist;          // [keys]          items per key                          (zeroed per call)
   int* ctrs;          // [8]             0 chunks, 1 in-view items, 2 unit cursor, 3 direct units,
-                      //                 5 chunk cursor of sample_params (zeroed)
+                      //                 5 work-item cursor of sample_params (zeroed)
   int* key_off;       // [keys]
   int* key_chunk0;    // [keys + 1]
   int* item_key;      // [items]
   int* item_rank;     // [items]
   int* sorted;        // [items]
   int4* chunks;       // [max_chunks]    {first, count, frame-view, key}
-  int4* bbox;         // [max_chunks * 8 * LV]   {x0, y0, width, height} texels
-  int* direct_list;   // [max_chunks * 8]
-  uint8_t* direct_flag;  // [max_chunks * 8]
+  int4* bbox;         // [max_chunks * 8 * LV]   {65535 - min x0, 65535 - min y0, max x0 + 1, max y0 + 1} of the
+                      //                 2x2 sample blocks: zeroed with the counters, reduced with atomicMax
+  int* direct_list;   // [max_chunks * 8]  units whose boxes exceed the shared-memory regions (gather_tiles -> gather_direct)
   uint2* params;      // [8 heads][LV][items][2 block columns][8 slots]   {x0 | y0 << 16, half2(w_top, w_bottom)}
   int keys, kx, ky, max_chunks;
   int64_t items;
+  int64_t zero_bytes; // counts | hist | ctrs | bbox: one memset per call
 };
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -114,15 +118,15 @@ static int64_t make_ws(const MvgSampleParams& p, void* base, GatherWs* w) {
   w->counts = reinterpret_cast<int*>(take(4 * (BV + keys + 8)));        // counts | hist | ctrs: one memset
   w->hist = w->counts ? w->counts + BV : nullptr;
   w->ctrs = w->counts ? w->hist + keys : nullptr;
+  w->bbox = reinterpret_cast<int4*>(take(16 * max_chunks * kHeads * p.num_levels));
+  w->zero_bytes = off;
   w->key_off = reinterpret_cast<int*>(take(4 * keys));
   w->key_chunk0 = reinterpret_cast<int*>(take(4 * (keys + 1)));
   w->item_key = reinterpret_cast<int*>(take(4 * items));
   w->item_rank = reinterpret_cast<int*>(take(4 * items));
   w->sorted = reinterpret_cast<int*>(take(4 * items));
   w->chunks = reinterpret_cast<int4*>(take(16 * max_chunks));
-  w->bbox = reinterpret_cast<int4*>(take(16 * max_chunks * kHeads * p.num_levels));
   w->direct_list = reinterpret_cast<int*>(take(4 * max_chunks * kHeads));
-  w->direct_flag = reinterpret_cast<uint8_t*>(take(max_chunks * kHeads));
   w->params = reinterpret_cast<uint2*>(take(8 * items * kHeads * p.num_levels * 16));
   w->keys = static_cast<int>(keys);
   w->kx = kx;
@@ -365,14 +369,27 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
   uint2* const rec_lane = ws.params + static_cast<int64_t>(m) * LV * ws.items * 16 + sub * 2;
   const int64_t lvl_stride = ws.items * 16;
   __shared__ int s_chunk;
+  __shared__ int s_item[kPart];
+  __shared__ float2 s_ref[kPart];
 #pragma unroll 1
   for (;;) {
-    __syncthreads();                     // previous chunk's boxes were written out, s_chunk was read
-    if (threadIdx.x == 0) s_chunk = atomicAdd(ws.ctrs + 5, 1);      // work queue: chunks differ in size
+    __syncthreads();                     // previous work item's boxes were written out, s_chunk was read
+    // work queue over (chunk, part of kPart items): a whole chunk per CTA is ~50 us of work and left
+    // the SMs idle for a fifth of the kernel (296 CTAs, ~2.5 chunks each)
+    if (threadIdx.x == 0) s_chunk = atomicAdd(ws.ctrs + 5, 1);
     __syncthreads();
-    const int chunk = s_chunk;
+    const int chunk = s_chunk / kParts, part = s_chunk % kParts;
     if (chunk >= nchunks) break;
     const int4 ch = ws.chunks[chunk];
+    const int i0 = part * kPart, i1 = min(i0 + kPart, ch.y);
+    if (i0 >= i1) continue;
+    // ids + reference points of the work item's items: one dependent global-load chain per CTA and work
+    // item instead of one per warp and item (it showed up as 8 % of the stall samples)
+    if (threadIdx.x < i1 - i0) {
+      const int it = ws.sorted[ch.x + i0 + threadIdx.x];
+      s_item[threadIdx.x] = it;
+      if (refl_in == nullptr) s_ref[threadIdx.x] = __ldg(reinterpret_cast<const float2*>(ref2d) + it);
+    }
     for (int i = threadIdx.x; i < kHeads * LV * 4; i += blockDim.x)
       (&s_bb[0][0][0])[i] = (i & 2) ? INT_MIN : INT_MAX;
     __syncthreads();
@@ -384,19 +401,13 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
     const __half* grow = gmap + static_cast<int64_t>(v * B + b) * prm.spatial_size * ldg + lane * 8;
     const float* qrow = qproj + static_cast<int64_t>(b) * N * kQP + lane * 8;
     const int item_base = bv * N;
-    // software prefetch of the next item's id + reference point
     // (measured and dropped: a cross-item pipeline that keeps item i+1's 12 corner rows in flight during
-    //  item i's phase B - 168 registers, 12 warps per SM, 145 us vs 127 us for this version)
-    int item = 0;
-    float2 rr = make_float2(0.f, 0.f);
-    if (warp < ch.y) {
-      item = ws.sorted[ch.x + warp];
-      if (refl_in == nullptr) rr = __ldg(reinterpret_cast<const float2*>(ref2d) + item);
-    }
+    //  item i's phase B - 168 registers, 12 warps per SM, 145 us vs 127 us for this version; an L1
+    //  prefetch of those rows, 132 vs 127 us)
 #pragma unroll 1
-    for (int idx = warp; idx < ch.y; idx += kPWarps) {
+    for (int idx = i0 + warp; idx < i1; idx += kPWarps) {
       const int pos = ch.x + idx;
-      const int cur = item;
+      const int cur = s_item[idx - i0];
       const int n = cur - item_base;
       float refl_x[LV], refl_y[LV];
       if (refl_in != nullptr) {          // ProjAttn.forward entry: reference points are given
@@ -406,15 +417,12 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
           refl_y[l] = __ldg(refl_in + (static_cast<int64_t>(cur) * LV + l) * 2 + 1);
         }
       } else {
+        const float2 rr = s_ref[idx - i0];
 #pragma unroll
         for (int l = 0; l < LV; ++l) {
           refl_x[l] = rr.x * sxl[l];
           refl_y[l] = rr.y * syl[l];
         }
-      }
-      if (idx + kPWarps < ch.y) {
-        item = ws.sorted[pos + kPWarps];
-        if (refl_in == nullptr) rr = __ldg(reinterpret_cast<const float2*>(ref2d) + item);
       }
       // ---------------- phase A (a4 i+iii): sample the pre-projected map G at the reference point
       if (lane < kQP / 8) {
@@ -566,18 +574,14 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
       }
     }
     __syncthreads();
-    if (threadIdx.x < kHeads) {
-      const int h = threadIdx.x;
-      bool fits = true;
-#pragma unroll
-      for (int l = 0; l < LV; ++l) {
-        const int x0 = s_bb[h][l][0], y0 = s_bb[h][l][1];
-        const int bw = s_bb[h][l][2] + 2 - x0, bh = s_bb[h][l][3] + 2 - y0;
-        ws.bbox[(static_cast<int64_t>(chunk) * kHeads + h) * LV + l] = make_int4(x0, y0, bw, bh);
-        fits = fits && bw * bh <= region_cap<LV>(l);
+    // fold this work item's boxes into the chunk's (one thread per (head, level))
+    if (threadIdx.x < kHeads * LV) {
+      const int h = threadIdx.x / LV, l = threadIdx.x % LV;
+      if (s_bb[h][l][0] != INT_MAX) {
+        int* bb = reinterpret_cast<int*>(ws.bbox + (static_cast<int64_t>(chunk) * kHeads + h) * LV + l);
+        atomicMax(bb + 0, 65535 - s_bb[h][l][0]); atomicMax(bb + 1, 65535 - s_bb[h][l][1]);
+        atomicMax(bb + 2, s_bb[h][l][2] + 1); atomicMax(bb + 3, s_bb[h][l][3] + 1);
       }
-      ws.direct_flag[chunk * kHeads + h] = fits ? 0 : 1;
-      if (!fits) ws.direct_list[atomicAdd(ws.ctrs + 3, 1)] = chunk * kHeads + h;
     }
   }
 }
@@ -721,11 +725,20 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
         if (lane == 0) u = atomicAdd(ws.ctrs + 2, 1);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= n_units) { unit = -1; return; }
-        if (ws.direct_flag[u] != 0) continue;              // left to gather_direct_kernel
+        bool fits = true;
+#pragma unroll
+        for (int l = 0; l < LV; ++l) {
+          const int4 mm = ws.bbox[static_cast<int64_t>(u) * LV + l];       // encoded min / max of the 2x2 block origins
+          const int x0 = 65535 - mm.x, y0 = 65535 - mm.y;
+          box[l] = make_int4(x0, y0, mm.z + 1 - x0, mm.w + 1 - y0);
+          fits = fits && box[l].z * box[l].w <= region_cap<LV>(l);
+        }
+        if (!fits) {                                       // left to gather_direct_kernel
+          if (lane == 0) ws.direct_list[atomicAdd(ws.ctrs + 3, 1)] = u;
+          continue;
+        }
         unit = u;
         ch = ws.chunks[u / kHeads];
-#pragma unroll
-        for (int l = 0; l < LV; ++l) box[l] = ws.bbox[static_cast<int64_t>(u) * LV + l];
         return;
       }
     };
@@ -898,7 +911,8 @@ static int launch_gather(const __half* vhm, const __half* gmp, const float* qpro
     pattr_done = true;
   }
   const int64_t chunks_bound = ws.items / kChunk + ws.keys + 1;
-  const int pgrid = static_cast<int>(chunks_bound < MVG_P_MINBLK * kNumSMs ? chunks_bound : MVG_P_MINBLK * kNumSMs);
+  const int64_t parts_bound = chunks_bound * kParts;
+  const int pgrid = static_cast<int>(parts_bound < MVG_P_MINBLK * kNumSMs ? parts_bound : MVG_P_MINBLK * kNumSMs);
   sample_params_kernel<LV><<<pgrid, kPWarps * 32, psmem, st>>>(gmp, qproj, prm, ref2d, refl_in, ws);
   int rc = check_launch("mvg_project_sample_fused(sample_params)");
   if (rc != MVG_OK) return rc;
@@ -959,7 +973,7 @@ extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, c
   GatherWs ws;
   make_ws(*prm, workspace, &ws);
   const int64_t BV = static_cast<int64_t>(prm->batch) * prm->views;
-  cudaError_t e = cudaMemsetAsync(ws.counts, 0, sizeof(int) * (BV + ws.keys + 8), st);
+  cudaError_t e = cudaMemsetAsync(ws.counts, 0, static_cast<size_t>(ws.zero_bytes), st);
   if (e != cudaSuccess) {
     set_error("mvg_project_sample_fused: cudaMemsetAsync: %s", cudaGetErrorString(e));
     return MVG_ELAUNCH;
