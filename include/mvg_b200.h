@@ -186,6 +186,14 @@ MVG_API int mvg_project_sample_fused(const float* ref3d, const float* cams, cons
                              float* ref2d, uint8_t* bounding, const float* refl_in,
                              void* workspace, void* stream);
 
+/* The projection (a3) alone - DQDecoderLayer.project_ref_points (dq_decoder.py:331-397) for all V views in
+ * one launch, same arithmetic as inside mvg_project_sample_fused (`bounding` bit-exact): ref3d (B,N,3)
+ * world mm, cams (B,V,MVG_CAM_FLOATS) -> ref2d (B,V,N,2) fp32 normalised network-image coordinates,
+ * bounding (B,V,N) uint8.  Used by the training-mode layer (mvgformer_b200/training.py), where the
+ * sampling runs through mvg_deform_forward / mvg_deform_backward. */
+MVG_API int mvg_project_points(const float* ref3d, const float* cams, int batch, int views, int points,
+                       float img_w, float img_h, float* ref2d, uint8_t* bounding, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Integer path of the query filter (dq_decoder.py:596-656): threshold mask, torch.where
  * order, per-frame counts, padding to the max count with query id 0, stable sort by frame,

@@ -155,6 +155,52 @@ __device__ __forceinline__ int key_rank(int* hist, int key, uint32_t active) {
   return base + __popc(peers & ((1u << lane) - 1u));
 }
 
+// a3: one 3D point through one packed camera -> normalised network-image coordinates + the
+// `bounding` bit.  Non-contracted fp32 in the reference's op order (cameras.py:167-207,
+// dq_decoder.py:374-397, transforms.py:135-141): `bounding` is bit-exact.
+__device__ __forceinline__ bool project_point(const MvgCamera* cam, const float* __restrict__ x3, float img_w,
+                                              float img_h, float& rx, float& ry) {
+  const float dx = fsub(__ldg(x3 + 0), cam->T[0]);
+  const float dy = fsub(__ldg(x3 + 1), cam->T[1]);
+  const float dz = fsub(__ldg(x3 + 2), cam->T[2]);
+  const float xc = fadd(fadd(fmul(cam->R[0], dx), fmul(cam->R[1], dy)), fmul(cam->R[2], dz));
+  const float yc = fadd(fadd(fmul(cam->R[3], dx), fmul(cam->R[4], dy)), fmul(cam->R[5], dz));
+  const float zc = fadd(fadd(fmul(cam->R[6], dx), fmul(cam->R[7], dy)), fmul(cam->R[8], dz));
+  const float zden = fadd(zc, 1e-5f);
+  float y0 = fdiv(xc, zden), y1 = fdiv(yc, zden);
+  const float r2 = fadd(fmul(y0, y0), fmul(y1, y1));
+  const float r4 = fmul(r2, r2), r6 = fmul(fmul(r2, r2), r2);
+  const float radial = fadd(1.f, fadd(fadd(fmul(cam->k[0], r2), fmul(cam->k[1], r4)), fmul(cam->k[2], r6)));
+  const float tanv = fadd(fmul(cam->p[0], y1), fmul(cam->p[1], y0));
+  const float corr = fadd(radial, fmul(2.f, tanv));
+  y0 = fadd(fmul(y0, corr), fmul(cam->p[1], r2));
+  y1 = fadd(fmul(y1, corr), fmul(cam->p[0], r2));
+  float px = fadd(fmul(cam->f[0], y0), cam->c[0]);
+  float py = fadd(fmul(cam->f[1], y1), cam->c[1]);
+  const bool inb = (px >= 0.f) && (py >= 0.f) && (px < cam->wh[0]) && (py < cam->wh[1]);
+  px = fminf(fmaxf(px, -1.f), cam->clamp_max);
+  py = fminf(fmaxf(py, -1.f), cam->clamp_max);
+  const float ax = fadd(fadd(fmul(px, cam->aff[0]), fmul(py, cam->aff[1])), cam->aff[2]);
+  const float ay = fadd(fadd(fmul(px, cam->aff[3]), fmul(py, cam->aff[4])), cam->aff[5]);
+  rx = fdiv(ax, img_w);
+  ry = fdiv(ay, img_h);
+  return inb;
+}
+
+// The projection alone (training path, diagnostics): no binning, no gather.
+__global__ void __launch_bounds__(kPcThreads)
+project_points_kernel(const float* __restrict__ ref3d, const MvgCamera* __restrict__ cams, int V, int N,
+                      float img_w, float img_h, float* __restrict__ ref2d_out, uint8_t* __restrict__ bounding_out) {
+  const int bv = blockIdx.y;
+  const int n = blockIdx.x * kPcThreads + threadIdx.x;
+  if (n >= N) return;
+  const int64_t item = static_cast<int64_t>(bv) * N + n;
+  float rx, ry;
+  const bool inb = project_point(cams + bv, ref3d + (static_cast<int64_t>(bv / V) * N + n) * 3, img_w, img_h, rx, ry);
+  *reinterpret_cast<float2*>(ref2d_out + 2 * item) = make_float2(rx, ry);
+  bounding_out[item] = inb ? 1 : 0;
+}
+
 // ------------------------------------------------------------------ projection + binning
 // One block = 256 consecutive points of ONE (frame, view) pair bv = blockIdx.y.
 __global__ void __launch_bounds__(kPcThreads)
@@ -171,33 +217,8 @@ project_bin_kernel(const float* __restrict__ ref3d, const MvgCamera* __restrict_
   float rx = 0.f, ry = 0.f;
   if (n < N) {
     const int b = bv / V;
-    const MvgCamera* cam = cams + bv;   // (B,V) row-major == item / N
-    const float* x3 = ref3d + (static_cast<int64_t>(b) * N + n) * 3;
-    const float dx = fsub(__ldg(x3 + 0), cam->T[0]);
-    const float dy = fsub(__ldg(x3 + 1), cam->T[1]);
-    const float dz = fsub(__ldg(x3 + 2), cam->T[2]);
-    const float xc = fadd(fadd(fmul(cam->R[0], dx), fmul(cam->R[1], dy)), fmul(cam->R[2], dz));
-    const float yc = fadd(fadd(fmul(cam->R[3], dx), fmul(cam->R[4], dy)), fmul(cam->R[5], dz));
-    const float zc = fadd(fadd(fmul(cam->R[6], dx), fmul(cam->R[7], dy)), fmul(cam->R[8], dz));
-    const float zden = fadd(zc, 1e-5f);
-    float y0 = fdiv(xc, zden), y1 = fdiv(yc, zden);
-    const float r2 = fadd(fmul(y0, y0), fmul(y1, y1));
-    const float r4 = fmul(r2, r2), r6 = fmul(fmul(r2, r2), r2);
-    const float radial = fadd(1.f, fadd(fadd(fmul(cam->k[0], r2), fmul(cam->k[1], r4)),
-                                        fmul(cam->k[2], r6)));
-    const float tanv = fadd(fmul(cam->p[0], y1), fmul(cam->p[1], y0));
-    const float corr = fadd(radial, fmul(2.f, tanv));
-    y0 = fadd(fmul(y0, corr), fmul(cam->p[1], r2));
-    y1 = fadd(fmul(y1, corr), fmul(cam->p[0], r2));
-    float px = fadd(fmul(cam->f[0], y0), cam->c[0]);
-    float py = fadd(fmul(cam->f[1], y1), cam->c[1]);
-    inb = (px >= 0.f) && (py >= 0.f) && (px < cam->wh[0]) && (py < cam->wh[1]);
-    px = fminf(fmaxf(px, -1.f), cam->clamp_max);
-    py = fminf(fmaxf(py, -1.f), cam->clamp_max);
-    const float ax = fadd(fadd(fmul(px, cam->aff[0]), fmul(py, cam->aff[1])), cam->aff[2]);
-    const float ay = fadd(fadd(fmul(px, cam->aff[3]), fmul(py, cam->aff[4])), cam->aff[5]);
-    rx = fdiv(ax, prm.img_w);
-    ry = fdiv(ay, prm.img_h);
+    inb = project_point(cams + bv /* (B,V) row-major == item / N */, ref3d + (static_cast<int64_t>(b) * N + n) * 3,
+                        prm.img_w, prm.img_h, rx, ry);
     *reinterpret_cast<float2*>(ref2d_out + 2 * item) = make_float2(rx, ry);
     bounding_out[item] = inb ? 1 : 0;
   }
@@ -1004,4 +1025,16 @@ extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, c
     case 3: return launch_gather<3>(vhm, gmp, qproj, *prm, sp, ref2d, refl_in, ws, st);
     default: return launch_gather<4>(vhm, gmp, qproj, *prm, sp, ref2d, refl_in, ws, st);
   }
+}
+
+extern "C" int mvg_project_points(const float* ref3d, const float* cams, int batch, int views, int points,
+                                  float img_w, float img_h, float* ref2d, uint8_t* bounding, void* stream) {
+  using namespace mvg;
+  MVG_REQUIRE(ref3d && cams && ref2d && bounding, "mvg_project_points: null pointer");
+  MVG_REQUIRE(batch > 0 && views > 0 && points > 0, "mvg_project_points: empty shape");
+  MVG_REQUIRE(static_cast<int64_t>(batch) * views <= 65535, "mvg_project_points: batch * views > 65535");
+  const dim3 grid((points + kPcThreads - 1) / kPcThreads, static_cast<unsigned>(batch * views));
+  project_points_kernel<<<grid, kPcThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      ref3d, reinterpret_cast<const MvgCamera*>(cams), views, points, img_w, img_h, ref2d, bounding);
+  return check_launch("mvg_project_points");
 }

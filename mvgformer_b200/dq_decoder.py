@@ -65,6 +65,18 @@ def _use_ffn_chain() -> bool:
     return os.environ.get("MVG_FFN_CHAIN", "1") != "0" and get_backend() == "tcgen05"
 
 
+def _wants_autograd(module, *tensors) -> bool:
+    """Training mode, or gradients requested through any of `tensors` (lists are searched)."""
+    if not torch.is_grad_enabled():
+        return False
+    if module.training:
+        return True
+    flat = []
+    for t in tensors:
+        flat.extend(t if isinstance(t, (list, tuple)) else [t])
+    return any(isinstance(t, torch.Tensor) and t.requires_grad for t in flat)
+
+
 def _get_clones(module, N):
     return nn.ModuleList([copy.deepcopy(module) for _ in range(N)])
 
@@ -225,12 +237,11 @@ class DQDecoderLayer(nn.Module):
     # ------------------------------------------------------------------ the layer
     def _forward_ctx(self, tgt, query_pos, reference_points, ctx: DecoderContext, *,
                      threshold, indices=None, return_debug=False, shard=None):
-        if self.training or (torch.is_grad_enabled() and any(
-                t is not None and t.requires_grad for t in (tgt, query_pos, reference_points))):
+        if _wants_autograd(self, tgt, query_pos, reference_points):
             # the fused path detaches its inputs and applies no dropout: refuse to pretend
-            raise NotImplementedError(
-                "mvgformer_b200.DQDecoderLayer is inference-only (call .eval() and run under "
-                "torch.no_grad()); training goes through the op-level DeformFunction drop-in")
+            raise RuntimeError(
+                "DQDecoderLayer._forward_ctx is the fused inference path; training / autograd calls go "
+                "through DQDecoderLayer.forward or DQDecoder.forward (mvgformer_b200/training.py)")
         B, N, C = tgt.shape
         J = self.num_joints
         Q = N // J
@@ -320,7 +331,14 @@ class DQDecoderLayer(nn.Module):
     def forward(self, tgt, query_pos, reference_points, src_views, src_spatial_shapes,
                 level_start_index, meta, src_padding_mask=None, rgb_views=None,
                 output_dir='./', frame_id=None, indices=None, threshold=0.5, indices_all=None):
-        """Signature and 5-tuple of dq_decoder.py:850-853,1045."""
+        """Signature and 5-tuple of dq_decoder.py:850-853,1045.  In training mode (or when a gradient
+        is requested through the inputs) the differentiable path of training.py runs instead of the
+        fused inference kernels."""
+        if not isinstance(src_views, ops.PackedPyramid) and _wants_autograd(self, tgt, query_pos, list(src_views)):
+            from .training import layer_forward_train
+            cams = pack_cameras(meta, self.img_size, device=tgt.device)
+            return layer_forward_train(self, tgt, query_pos, reference_points, src_views, cams,
+                                       threshold=threshold, indices=indices)
         ctx = DecoderContext(src_views, meta, self.img_size, [self], tgt.shape[0])
         return self._forward_ctx(tgt, query_pos, reference_points, ctx, threshold=threshold,
                                  indices=indices)
@@ -367,7 +385,14 @@ class DQDecoder(nn.Module):
         of frame i execute); src_views / meta are then ignored."""
         if not tgt.is_cuda:
             raise RuntimeError("Not implemented on the CPU")
-        if ctx is None:
+        train = ctx is None and not isinstance(src_views, ops.PackedPyramid) and \
+            _wants_autograd(self, tgt, query_pos, reference_points, list(src_views))
+        if train:
+            if shard is not None:
+                raise NotImplementedError("query sharding is an inference feature")
+            from .training import layer_forward_train
+            cams = pack_cameras(meta, self.layers[0].img_size, device=tgt.device)
+        elif ctx is None:
             ctx = self.prepare(src_views, meta, tgt.shape[0])
         output = tgt
         inter, inter_ref, inter_2d, inter_proj, classes = [], [], [], [], []
@@ -378,9 +403,14 @@ class DQDecoder(nn.Module):
             if shard is not None:
                 force = len(shard) > 3 and shard[3] is not None and lid in shard[3]
                 lshard = (shard[0], shard[1], shard[2], force)
-            output, reference_points, ref_points_2d, projs_2d_absolute, outputs_class = \
-                layer._forward_ctx(output, query_pos, reference_points, ctx, threshold=threshold,
-                                   indices=indices, shard=lshard)
+            if train:
+                output, reference_points, ref_points_2d, projs_2d_absolute, outputs_class = \
+                    layer_forward_train(layer, output, query_pos, reference_points, src_views, cams,
+                                        threshold=threshold, indices=indices)
+            else:
+                output, reference_points, ref_points_2d, projs_2d_absolute, outputs_class = \
+                    layer._forward_ctx(output, query_pos, reference_points, ctx, threshold=threshold,
+                                       indices=indices, shard=lshard)
             if shard is not None:
                 counts.append(layer._shard_count)
             if self.return_intermediate:

@@ -138,6 +138,20 @@ def project_sample_fused(ref3d: Optional[torch.Tensor], cams: Optional[torch.Ten
     return sampled, ref2d, bounding, work
 
 
+def project_points(ref3d: torch.Tensor, cams: torch.Tensor, img_size) -> Tuple[torch.Tensor, torch.Tensor]:
+    """a3 alone: ref3d (B,N,3) fp32 world mm, cams (B,V,64) -> ref2d (B,V,N,2) fp32 normalised
+    network-image coordinates, bounding (B,V,N) uint8 (bit-exact with the fused kernel's)."""
+    _lib.require_cuda(ref3d, cams)
+    B, N, _ = ref3d.shape
+    V = cams.shape[1]
+    ref2d = torch.empty((B, V, N, 2), dtype=torch.float32, device=ref3d.device)
+    bounding = torch.empty((B, V, N), dtype=torch.uint8, device=ref3d.device)
+    _lib.check(_lib.load().mvg_project_points(_lib.ptr(ref3d), _lib.ptr(cams), B, V, N, float(img_size[0]),
+                                              float(img_size[1]), _lib.ptr(ref2d), _lib.ptr(bounding),
+                                              stream_ptr(ref3d.device)), "mvg_project_points")
+    return ref2d, bounding
+
+
 def select_pad(prob: torch.Tensor, threshold: float, method: str = "threshold",
                with_ids: bool = False, min_one: bool = True):
     """Integer path of dq_decoder.py:596-656.  -> selected (B,Q) uint8, counts (B) i32,

@@ -112,6 +112,37 @@ class ProjAttn(nn.Module):
         self._wcache = (key, pack)
         return pack
 
+    def forward_autograd(self, query, reference_points, src_views, spatial_shapes, level_start_index):
+        """The differentiable form of `forward` (training): the reference's own
+        sequence of steps (projattn.py:139-204) with the dense projections left to autograd and the
+        sampling done by `DeformFunction` - mvg_deform_forward, and mvg_deform_backward for the
+        gradients w.r.t. value, sampling locations and attention weights.  Includes the `.view` layout
+        scramble of :180-181.  query (n_views, Lq, C); reference_points (n_views, Lq, Lv or 1, 2);
+        src_views list of Lv (n_views, C, H_l, W_l); -> (n_views, Lq, C) float32."""
+        import torch.nn.functional as F
+        from .deform_func import DeformFunction
+        self._check_supported()
+        if not query.is_cuda:
+            raise RuntimeError("Not implemented on the CPU")
+        nv, Lq, C = query.shape
+        Lv = len(src_views)
+        M, P = self.n_heads, self.n_points
+        ref = reference_points.float().expand(-1, -1, Lv, -1)
+        grid = torch.clamp(ref * 2.0 - 1.0, -1.1, 1.1)
+        feats = [F.grid_sample(src_views[l].float(), grid[:, :, l:l + 1, :], align_corners=False)
+                 .squeeze(-1).permute(0, 2, 1) for l in range(Lv)]                      # :139-153
+        flat = torch.cat([s.flatten(2) for s in src_views], dim=-1).permute(0, 2, 1).float()
+        value = self.rayconv(flat).view(nv, -1, M, C // M)                             # :160-168
+        x = torch.stack(feats, dim=2) + query.float().unsqueeze(2)                     # (nv,Lq,Lv,C)
+        off = self.sampling_offsets(x).view(nv, Lq, M, Lv, P, 2)                        # :180
+        attn = F.softmax(self.attention_weights(x).view(nv, Lq, M, Lv * P), -1).view(nv, Lq, M, Lv, P)
+        normalizer = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1).float()
+        loc = ref[:, :, None, :, None, :] + off / normalizer[None, None, None, :, None, :]   # :186-191
+        sampled = DeformFunction.apply(value.contiguous(), spatial_shapes.contiguous(),
+                                       level_start_index.contiguous(), loc.contiguous(),
+                                       attn.contiguous(), self.im2col_step)
+        return self.output_proj(sampled)
+
     def forward(self, query, reference_points, src_views, camera_ray_embeds,
                 input_spatial_shapes, input_level_start_index, input_padding_mask=None):
         """query (n_views, Lq, C); reference_points (n_views, Lq, Lv, 2) in [0,1];
@@ -127,6 +158,10 @@ class ProjAttn(nn.Module):
                                       "(lib/models/dq_decoder.py:577)")
         if not query.is_cuda:
             raise RuntimeError("Not implemented on the CPU")
+        if torch.is_grad_enabled() and (self.training or query.requires_grad or reference_points.requires_grad
+                                        or any(s.requires_grad for s in src_views)):
+            return self.forward_autograd(query, reference_points, src_views, input_spatial_shapes,
+                                         input_level_start_index)
         n_views, Lq, _ = query.shape
         levels = [(int(s.shape[2]), int(s.shape[3])) for s in src_views]
         Len_in = sum(h * w for h, w in levels)

@@ -53,15 +53,31 @@ with torch.no_grad():
     prm = ops.make_sample_params(B, V, N, ctx.levels, ctx.ld_g, ctx.img_size, ctx.value_head_stride)
     ref3d = ref.reshape(B, N, 3).float().contiguous()
     for _ in range(3):
-        sampled, ref2d, bounding = ops.project_sample_fused(ref3d, ctx.cams, value_hm, gmap, qproj, prm)
+        sampled, ref2d, bounding, work = ops.project_sample_fused(ref3d, ctx.cams, value_hm, gmap, qproj, prm)
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(a.iters):
-        sampled, ref2d, bounding = ops.project_sample_fused(ref3d, ctx.cams, value_hm, gmap, qproj, prm)
+        sampled, ref2d, bounding, work = ops.project_sample_fused(ref3d, ctx.cams, value_hm, gmap, qproj, prm)
     e.record()
     torch.cuda.synchronize()
     us = s.elapsed_time(e) * 1e3 / a.iters
     frac = float(bounding.float().mean())
     print(f"project_sample_fused: {us:.1f} us / call, in-view fraction {frac:.3f}, "
           f"{us / (frac * B * V * N) * 1e3:.2f} ns per gathered item, checksum {float(sampled.float().abs().mean()):.5f}")
+
+    # binning statistics of the call (workspace head: counts[BV] | hist[keys] | ctrs[8])
+    BV = B * V
+    kx, ky = (ctx.levels[0][1] + 19) // 20, (ctx.levels[0][0] + 19) // 20
+    keys = BV * kx * ky
+    w = work.view(torch.int32)
+    hist = w[BV:BV + keys].cpu().numpy()
+    ctrs = w[BV + keys:BV + keys + 8].cpu().numpy()
+    nz = hist[hist > 0]
+    nch = ((nz + 127) // 128).sum()
+    print(f"keys {keys}, non-empty {len(nz)}, items {nz.sum()}, chunks {ctrs[0]} (={nch}), mean chunk {nz.sum() / max(nch, 1):.1f}, "
+          f"direct units {ctrs[3]}; key-size percentiles 10/50/90/max: {np.percentile(nz, 10):.0f} {np.percentile(nz, 50):.0f} "
+          f"{np.percentile(nz, 90):.0f} {nz.max()}")
+    sizes = np.concatenate([np.full((c + 127) // 128, -(-c // ((c + 127) // 128))) for c in nz])
+    print("chunk size histogram (<=32, <=64, <=96, <=128):", [(sizes <= 32).sum(), ((sizes > 32) & (sizes <= 64)).sum(),
+          ((sizes > 64) & (sizes <= 96)).sum(), (sizes > 96).sum()])
