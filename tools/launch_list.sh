@@ -4,7 +4,7 @@
 tag=${1:-x}
 mkdir -p gpurun_out
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"bin_|project_bin|sample_params|gather_" -c 60 --csv \
-  --log-file gpurun_out/gather_launches_$tag.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-graph \
+  --log-file gpurun_out/gather_launches_$tag.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-graph --no-parity ${LL_ARGS} \
   > gpurun_out/gather_launches_$tag.log 2>&1
 python - <<PY
 import csv, collections
