@@ -66,9 +66,12 @@ constexpr int kChunk = 128;        // items per chunk (upper bound)
 #define MVG_P_MINBLK 2
 #endif
 constexpr int kPWarps = MVG_P_WARPS;   // sample_params: warps per CTA
-constexpr int kGWarps = 16;        // gather_tiles: consumer warps per CTA (+ 1 producer warp)
+#ifndef MVG_G_WARPS
+#define MVG_G_WARPS 16
+#endif
+constexpr int kGWarps = MVG_G_WARPS;   // gather_tiles: consumer warps per CTA (+ 1 producer warp)
 constexpr int kScanThreads = 1024;
-constexpr int kIPW = kChunk / kGWarps;   // items per consumer warp and unit
+constexpr int kIPW = (kChunk + kGWarps - 1) / kGWarps;   // items per consumer warp and unit
 constexpr int kPart = 32;          // sample_params work item: kPart items of one chunk
 constexpr int kParts = kChunk / kPart;
 constexpr int kRecBytes = 128;     // records of one (item, head, level): 2 block columns x 8 points x 8 B
@@ -847,10 +850,11 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
 #pragma unroll
         for (int k = 0; k < kIPW; k += 2) {
           const int ia = warp + kGWarps * k;
-          if (ia + kGWarps < count) {                  // warp-uniform: both items exist
+          constexpr int kLast = kIPW - 1;                // an odd kIPW leaves the last item without a partner
+          if (k < kLast && ia + kGWarps < count) {       // warp-uniform: both items exist
             const uint4 ra = lds128(rcs + static_cast<uint32_t>(k * kGWarps) * kRecBytes);
             const uint4 rb = lds128(rcs + static_cast<uint32_t>((k + 1) * kGWarps) * kRecBytes);
-            blend_pair(ra, rb, tile, box.z, acc[k], acc[k + 1]);
+            blend_pair(ra, rb, tile, box.z, acc[k], acc[k < kLast ? k + 1 : k]);
           } else if (ia < count) {
             const uint4 rc = lds128(rcs + static_cast<uint32_t>(k * kGWarps) * kRecBytes);
             blend_two<true>(rc, tile, nullptr, box.z, acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
