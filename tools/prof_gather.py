@@ -81,3 +81,15 @@ with torch.no_grad():
     sizes = np.concatenate([np.full((c + 127) // 128, -(-c // ((c + 127) // 128))) for c in nz])
     print("chunk size histogram (<=32, <=64, <=96, <=128):", [(sizes <= 32).sum(), ((sizes > 32) & (sizes <= 64)).sum(),
           ((sizes > 64) & (sizes <= 96)).sum(), (sizes > 96).sum()])
+    # boxes of the (chunk, head, level) units: workspace layout of make_ws (counts|hist|ctrs padded to 256 B, then bbox)
+    head_bytes = (4 * (BV + keys + 8) + 255) // 256 * 256
+    nchunks = int(ctrs[0])
+    bb = w[head_bytes // 4: head_bytes // 4 + nchunks * 8 * 3 * 4].cpu().numpy().reshape(nchunks, 8, 3, 4)
+    x0, y0 = 65535 - bb[..., 0], 65535 - bb[..., 1]
+    bw, bh = bb[..., 2] + 1 - x0, bb[..., 3] + 1 - y0
+    for l in range(3):
+        a, b = bw[:, :, l].ravel(), bh[:, :, l].ravel()
+        print(f"level {l}: box width p50/p90/p99/max {np.percentile(a, 50):.0f} {np.percentile(a, 90):.0f} {np.percentile(a, 99):.0f} {a.max()}"
+              f" | height {np.percentile(b, 50):.0f} {np.percentile(b, 90):.0f} {np.percentile(b, 99):.0f} {b.max()}"
+              f" | area p50/p90/max {np.percentile(a * b, 50):.0f} {np.percentile(a * b, 90):.0f} {(a * b).max()}"
+              f" | max(w,h) > 39/32/24: {(np.maximum(a, b) > 39).mean():.3f} {(np.maximum(a, b) > 32).mean():.3f} {(np.maximum(a, b) > 24).mean():.3f}")
