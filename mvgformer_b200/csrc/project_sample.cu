@@ -662,9 +662,22 @@ __device__ __forceinline__ void blend_pair(const uint4 ra, const uint4 rb, uint3
   const uint32_t pa1 = sbase + (ya1 * static_cast<uint32_t>(bw) + xa1) * 64u;
   const uint32_t pb0 = sbase + (yb0 * static_cast<uint32_t>(bw) + xb0) * 64u;
   const uint32_t pb1 = sbase + (yb1 * static_cast<uint32_t>(bw) + xb1) * 64u;
+#ifdef MVG_ABL_NOLDS      // timing experiment only (wrong results): no tile loads
+  const uint4 ta0 = make_uint4(pa0, pa0, pa0, pa0), ba0 = make_uint4(bw64, pa0, bw64, pa0), ta1 = make_uint4(pa1, pa1, pa1, pa1), ba1 = ba0;
+  const uint4 tb0 = make_uint4(pb0, pb0, pb0, pb0), bb0 = ba0, tb1 = make_uint4(pb1, pb1, pb1, pb1), bb1 = ba0;
+#else
   const uint4 ta0 = lds128(pa0), ba0 = lds128(pa0 + bw64), ta1 = lds128(pa1), ba1 = lds128(pa1 + bw64);
   const uint4 tb0 = lds128(pb0), bb0 = lds128(pb0 + bw64), tb1 = lds128(pb1), bb1 = lds128(pb1 + bw64);
+#endif
+#ifdef MVG_ABL_NOBLEND    // timing experiment only (wrong results): one LOP3 per loaded register pair instead of two HFMA2
   auto blend = [](const uint4& top, const uint4& bot, uint32_t rw, __half2 (&c)[4]) {
+    c[0] = u32_as_half2(half2_as_u32(c[0]) ^ top.x ^ bot.x); c[1] = u32_as_half2(half2_as_u32(c[1]) ^ top.y ^ bot.y);
+    c[2] = u32_as_half2(half2_as_u32(c[2]) ^ top.z ^ bot.z); c[3] = u32_as_half2(half2_as_u32(c[3]) ^ top.w ^ (bot.w + rw));
+  };
+  auto blend_unused = [](const uint4& top, const uint4& bot, uint32_t rw, __half2 (&c)[4]) {
+#else
+  auto blend = [](const uint4& top, const uint4& bot, uint32_t rw, __half2 (&c)[4]) {
+#endif
     const __half2 w = u32_as_half2(rw);
     const __half2 wt = __low2half2(w), wb = __high2half2(w);
     c[0] = __hfma2(wt, u32_as_half2(top.x), c[0]); c[0] = __hfma2(wb, u32_as_half2(bot.x), c[0]);
@@ -736,41 +749,55 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
 
   if (warp == kGWarps) {
     // ===================== producer: unit descriptors, tile rows, record blocks =====================
-    // The next unit's metadata (work-queue ticket, chunk, boxes) is fetched right after this unit's
-    // level-0 copies are issued, so its global-memory latency hides behind the copies in flight.
+    // The unit metadata runs through a three-stage pipeline - work-queue ticket (atomicAdd) -> loads of
+    // that unit's chunk + boxes -> use - so that the staging loop never waits for a global round trip:
+    // with a blocking fetch per unit (atomic, then dependent loads: ~2 us) on top of ~70 bulk copies at
+    // ~30 ns each the producer warp needed ~4 us per unit against ~5 us of consumption, and tile staging
+    // hardly overlapped the gather (ablation: the kernel without any loads / blends still took 103 us).
     // (Sharing one set of tiles between the chunks of a dense key was measured and dropped: the
     //  union boxes grow and a 4-chunk work item unbalances the tail - 189 -> 209 us.)
     const int n_units = ws.ctrs[0] * kHeads;
-    int unit = -1;
-    int4 ch = make_int4(0, 0, 0, 0), box[LV];
-    auto fetch = [&]() {
-      for (;;) {
-        int u = 0;
-        if (lane == 0) u = atomicAdd(ws.ctrs + 2, 1);
-        u = __shfl_sync(0xffffffffu, u, 0);
-        if (u >= n_units) { unit = -1; return; }
-        bool fits = true;
+    int tk = 0;                                  // lane 0: ticket whose loads are not issued yet
+    int lu = 0;                                  // unit whose loads are in flight
+    int4 lch = make_int4(0, 0, 0, 0), lmm[LV];
+    auto take_ticket = [&]() { if (lane == 0) tk = atomicAdd(ws.ctrs + 2, 1); };
+    auto issue_loads = [&]() {
+      lu = __shfl_sync(0xffffffffu, tk, 0);
+      if (lu < n_units) {
+        lch = ws.chunks[lu / kHeads];
 #pragma unroll
-        for (int l = 0; l < LV; ++l) {
-          const int4 mm = ws.bbox[static_cast<int64_t>(u) * LV + l];       // encoded min / max of the 2x2 block origins
-          const int x0 = 65535 - mm.x, y0 = 65535 - mm.y;
-          box[l] = make_int4(x0, y0, mm.z + 1 - x0, mm.w + 1 - y0);
-          fits = fits && box[l].z * box[l].w <= region_cap<LV>(l);
-        }
-        // (measured and dropped: also sending chunks of < 16 / 32 / 64 items to gather_direct_kernel to save
-        //  their tile staging - the direct kernel costs 4-8x more per item: +70 / +95 / +160 us at Q = 1024)
-        if (!fits) {                                       // left to gather_direct_kernel
-          if (lane == 0) ws.direct_list[atomicAdd(ws.ctrs + 3, 1)] = u;
-          continue;
-        }
-        unit = u;
-        ch = ws.chunks[u / kHeads];
-        return;
+        for (int l = 0; l < LV; ++l) lmm[l] = ws.bbox[static_cast<int64_t>(lu) * LV + l];
       }
     };
-    fetch();
+    take_ticket();
+    issue_loads();
+    take_ticket();
     uint32_t seq = 0;
     for (;;) {
+      // ---- use stage: the next unit whose boxes fit the regions
+      int unit;
+      int4 ch, box[LV];
+      for (;;) {
+        unit = lu;
+        ch = lch;
+        bool fits = true;
+        if (unit < n_units) {
+#pragma unroll
+          for (int l = 0; l < LV; ++l) {
+            const int4 mm = lmm[l];                          // encoded min / max of the 2x2 block origins
+            const int x0 = 65535 - mm.x, y0 = 65535 - mm.y;
+            box[l] = make_int4(x0, y0, mm.z + 1 - x0, mm.w + 1 - y0);
+            fits = fits && box[l].z * box[l].w <= region_cap<LV>(l);
+          }
+        }
+        issue_loads();                                       // loads of the ticket taken one step ago
+        take_ticket();
+        if (unit >= n_units) { unit = -1; break; }
+        if (fits) break;
+        // (measured and dropped: also sending chunks of < 16 / 32 / 64 items to gather_direct_kernel to save
+        //  their tile staging - the direct kernel costs 4-8x more per item: +70 / +95 / +160 us at Q = 1024)
+        if (lane == 0) ws.direct_list[atomicAdd(ws.ctrs + 3, 1)] = unit;      // left to gather_direct_kernel
+      }
       const uint32_t par = seq & 1u;
       mbar_wait(&empty[0], par ^ 1u);      // level 0 of unit seq-1 consumed => descriptor slot (seq & 1) is free
       UnitDesc* d = &sdesc[par];
@@ -790,13 +817,10 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
       __syncwarp();
       const __half* vh = value_hm + static_cast<int64_t>(head) * prm.value_head_stride;
       const uint2* rec_src = ws.params + (static_cast<int64_t>(head) * LV * ws.items + first) * 16;
-      int4 cbox[LV];
-#pragma unroll
-      for (int l = 0; l < LV; ++l) cbox[l] = box[l];
 #pragma unroll
       for (int l = 0; l < LV; ++l) {
         if (l > 0) mbar_wait(&empty[l], par ^ 1u);
-        const int bw = cbox[l].z, bh = cbox[l].w;
+        const int bw = box[l].z, bh = box[l].w;
         const uint32_t row_bytes = static_cast<uint32_t>(bw) * 64u;
         const uint32_t rec_bytes = static_cast<uint32_t>(count) * kRecBytes;
 #ifdef MVG_DEBUG_NOSTAGE      // timing experiment only (wrong results): tiles are staged for the first unit only
@@ -809,11 +833,10 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
           bulk_g2s(recs[l], rec_src + static_cast<int64_t>(l) * ws.items * 16, rec_bytes, &full[l]);
         }
         __syncwarp();
-        const __half* src0 = vh + (vrow0 + prm.level_start[l] + static_cast<int64_t>(cbox[l].y) * prm.level_w[l] + cbox[l].x) * 32;
+        const __half* src0 = vh + (vrow0 + prm.level_start[l] + static_cast<int64_t>(box[l].y) * prm.level_w[l] + box[l].x) * 32;
         for (int r = lane; r < bh_eff; r += 32)
           bulk_g2s(region[l] + static_cast<uint32_t>(r) * row_bytes, src0 + static_cast<int64_t>(r) * prm.level_w[l] * 32,
                    row_bytes, &full[l]);
-        if (l == 0) fetch();               // overwrites unit / ch / box: cbox, first, count, head are this unit's
       }
       ++seq;
     }
@@ -845,6 +868,9 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
         const uint32_t tile = region[l] + static_cast<uint32_t>(lane & 7) * 16u -
                               static_cast<uint32_t>(box.y * box.z + box.x) * 64u;
         const uint32_t rcs = recs[l] + rec_lane + static_cast<uint32_t>(warp) * kRecBytes;
+#ifdef MVG_ABL_NOREC
+        const uint4 rec0 = lds128(rcs);
+#endif
         // items in pairs: inside a pair both record loads, then all eight tile loads are issued before
         // the blends, so the shared-memory latency of one item hides behind the other's arithmetic
 #pragma unroll
@@ -852,8 +878,12 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
           const int ia = warp + kGWarps * k;
           constexpr int kLast = kIPW - 1;                // an odd kIPW leaves the last item without a partner
           if (k < kLast && ia + kGWarps < count) {       // warp-uniform: both items exist
+#ifdef MVG_ABL_NOREC      // timing experiment only (wrong results): one record per warp and level
+            const uint4 ra = rec0, rb = rec0;
+#else
             const uint4 ra = lds128(rcs + static_cast<uint32_t>(k * kGWarps) * kRecBytes);
             const uint4 rb = lds128(rcs + static_cast<uint32_t>((k + 1) * kGWarps) * kRecBytes);
+#endif
             blend_pair(ra, rb, tile, box.z, acc[k], acc[k < kLast ? k + 1 : k]);
           } else if (ia < count) {
             const uint4 rc = lds128(rcs + static_cast<uint32_t>(k * kGWarps) * kRecBytes);

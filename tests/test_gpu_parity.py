@@ -253,6 +253,10 @@ def test_projection_bit_exact_and_fused_sampling():
             # bf16 value map + bf16 output; a handful of samples may straddle a texel border
             assert float(err.mean()) < 6e-3 and float(err.quantile(0.999)) < 6e-2, (float(err.mean()), float(err.max()))
         assert n_out > 0
+        # the stand-alone projection (training path) is the same arithmetic: bit-identical outputs
+        cams = mvg.cameras.pack_cameras(scd["meta"], sc["img_size"], device=DEV)
+        r2, b2 = ops.project_points(scd["reference_points"].float().contiguous(), cams, sc["img_size"])
+        assert torch.equal(r2, dbg["ref2d"]) and torch.equal(b2, dbg["bounding"])
 
 
 def test_projattn_module_vs_reference_golden():

@@ -149,3 +149,27 @@ def test_decoder_training_mode_runs_all_layers_with_dropout():
     with torch.no_grad():
         hs_eval = dec(*args, query_pos=sc["query_pos"].to(DEV), threshold=0.1)[0]
     assert hs_eval.shape == hs.shape and not hs_eval.requires_grad
+
+
+def test_training_with_matcher_indices_and_empty_selection():
+    """`indices` from the matcher choose the triangulated queries (dq_decoder.py:899-903); an empty list
+    falls back to query 0 of frame 0 (:620-623).  Unselected queries keep zero poses and get no gradient
+    through the DLT."""
+    B, V, Q = 2, 3, 8
+    levels = ((20, 36), (10, 18), (5, 9))
+    sc = syn.make_scene(batch=B, n_views=V, num_instance=Q, seed=23, levels=levels)
+    sd = syn.make_decoder_state_dict(1, np.random.default_rng(5), offset_px=1.0)
+    layer = make_decoder(sc, sd, 1).layers[0].train()
+    feats = [s.to(DEV) for s in sc["src_views"]]
+    common = (sc["query_pos"].to(DEV), sc["reference_points"].to(DEV), feats, sc["spatial_shapes"].to(DEV),
+              sc["level_start_index"].to(DEV), _to_dev(sc["meta"]))
+    for indices, expect in (([[1, 5], [3]], {(0, 1), (0, 5), (1, 3)}), ([[], []], {(0, 0)})):
+        tgt = sc["tgt"].to(DEV).requires_grad_(True)
+        out = layer(tgt, *common, indices=indices, threshold=0.1)
+        poses = out[1].view(B, Q, 15, 3)
+        nz = {(int(b), int(q)) for b, q in zip(*torch.where(poses.abs().sum((-1, -2)) > 0))}
+        assert nz == expect, (nz, expect)
+        poses.sum().backward()
+        g = tgt.grad.view(B, Q, 15, 256).abs().sum((-1, -2))
+        got = {(int(b), int(q)) for b, q in zip(*torch.where(g > 0))}
+        assert got == expect, (got, expect)        # pose gradients only reach the triangulated queries
