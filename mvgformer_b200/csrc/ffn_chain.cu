@@ -3,8 +3,11 @@
 //
 //   t2  = aver @ Wfu^T + bfu                      tcgen05, fp32 accumulator in TMEM
 //   tu  = LayerNorm2(tgt + t2)                    epilogue: row statistics straight from TMEM
-//   h_c = relu(tu @ W1[c]^T + b1[c])   c = 0..3   hidden layer in 256-column chunks, bf16 in smem
+//   h_c = relu(tu @ W1[c]^T + b1[c])   c = 0..7   hidden layer in 128-column chunks, bf16 in smem
 //   y  += h_c @ W2[:, c]^T                        second accumulator in TMEM
+// The hidden chunks are software-pipelined: two 128-column accumulators and two h buffers alternate, so
+// that the MMA warp issues chunk c+1's GEMM while the epilogue warps turn chunk c into relu(h_c) (with
+// 256-column chunks and one accumulator the tensor pipe idled through every epilogue: 18 % busy).
 //   out = LayerNorm3(tu + y + b2)
 //
 // Before this kernel the chain was 6 launches (3 GEMMs + 2 LayerNorm kernels + their bf16 / fp32
@@ -25,6 +28,8 @@ constexpr int kFcStages = 3;
 constexpr int kFcStageBytes = 256 * kBlockK * 2;        // 32 KB: 256 weight rows x 64 K
 constexpr int kFcPanelBytes = kBlockM * kBlockK * 2;    // 16 KB: 128 rows x 64 K
 constexpr int kFcActBytes = 4 * kFcPanelBytes;          // 64 KB: a 128 x 256 bf16 activation tile
+constexpr int kFcHBytes = 2 * kFcPanelBytes;            // 32 KB: one 128 x 128 bf16 hidden chunk
+constexpr int kFcHC = 128;                              // hidden columns per chunk
 constexpr int kFcThreads = 10 * 32;
 constexpr int kFcSmemBytes = 2 * kFcActBytes + kFcStages * kFcStageBytes + 2048 /*stats*/ + 256 /*barriers*/;
 static_assert(kFcSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
@@ -66,7 +71,7 @@ struct FfnChainParams {
   const float* e3;
   float* out;              // (M, 256) fp32; also holds tu between the two LayerNorms
   int M;
-  int n_chunks;            // d_ffn / 256
+  int n_chunks;            // d_ffn / 128
   float eps2, eps3;
 };
 
@@ -166,13 +171,14 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint64_t* w_empty = bars + kFcStages;      // [kFcStages]
   uint64_t* x_full = bars + 2 * kFcStages;
   uint64_t* x_free = x_full + 1;
-  uint64_t* acc1_full = x_full + 2;
+  uint64_t* g0_full = x_full + 2;            // t2 (all 256 columns of acc1)
   uint64_t* acc2_full = x_full + 3;
   uint64_t* acc2_free = x_full + 4;
   uint64_t* tu_ready = x_full + 5;
-  uint64_t* h_ready = x_full + 6;
-  uint64_t* h_free = x_full + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 8);
+  uint64_t* a1_full = x_full + 6;            // [2] hidden-chunk accumulator b holds tu W1[c]^T
+  uint64_t* h_ready = x_full + 8;            // [2] relu(h_c) is in h buffer b, accumulator b is free
+  uint64_t* h_free = x_full + 10;            // [2] the y GEMM has read h buffer b
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
@@ -189,12 +195,15 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
     mbar_init(x_full, 1);
     mbar_init(x_free, 1);
-    mbar_init(acc1_full, 1);
+    mbar_init(g0_full, 1);
     mbar_init(acc2_full, 1);
     mbar_init(acc2_free, 8);
     mbar_init(tu_ready, 8);
-    mbar_init(h_ready, 8);
-    mbar_init(h_free, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&a1_full[b], 1);
+      mbar_init(&h_ready[b], 8);
+      mbar_init(&h_free[b], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -226,51 +235,104 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int kb = 0; kb < 4; ++kb)
           tma_load_2d(&tmap_x, x_full, xbuf + kb * kFcPanelBytes, kb * kBlockK, mt * kBlockM);
         for (int kb = 0; kb < 4; ++kb) load_w(&tmap_fu, kb * kBlockK, 0);
+        // W1 chunk: 128 rows x 256 K = two stages of two 128 x 64 boxes; W2 chunk: 256 rows x 128 K = two
+        // stages.  Same order as the MMA warp issues them: W1(0), then W1(c+1), W2(c).
+        auto load_w1 = [&](int c) {
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int s = ws % kFcStages;
+            mbar_wait(&w_empty[s], ((ws / kFcStages) & 1) ^ 1);
+            mbar_expect_tx(&w_full[s], kFcStageBytes);
+            tma_load_2d(&tmap_w1, &w_full[s], wbuf + s * kFcStageBytes, (2 * s2) * kBlockK, c * kFcHC);
+            tma_load_2d(&tmap_w1, &w_full[s], wbuf + s * kFcStageBytes + kFcPanelBytes, (2 * s2 + 1) * kBlockK,
+                        c * kFcHC);
+            ++ws;
+          }
+        };
+        load_w1(0);
         for (int c = 0; c < NCH; ++c) {
-          for (int kb = 0; kb < 4; ++kb) load_w(&tmap_w1, kb * kBlockK, c * 256);
-          for (int kb = 0; kb < 4; ++kb) load_w(&tmap_w2, c * 256 + kb * kBlockK, 0);
+          if (c + 1 < NCH) load_w1(c + 1);
+          for (int j = 0; j < 2; ++j) load_w(&tmap_w2, c * kFcHC + j * kBlockK, 0);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(256);
+      const uint32_t idesc = make_idesc_bf16(256), idesc_h = make_idesc_bf16(kFcHC);
       uint32_t ws = 0, it = 0, hc = 0;
-      // one 128 x 256 x 256 GEMM: A = 4 K-panels at `abuf`, B = the next 4 weight stages
-      auto gemm = [&](uint8_t* abuf, uint32_t tmem_d, bool fresh) {
+      // t2: one 128 x 256 x 256 GEMM, A = 4 K-panels of xbuf, B = the next 4 weight stages
+      auto gemm0 = [&]() {
         for (int kb = 0; kb < 4; ++kb, ++ws) {
           const int s = ws % kFcStages;
           mbar_wait(&w_full[s], (ws / kFcStages) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = make_smem_desc_sw128(smem_u32(abuf + kb * kFcPanelBytes));
+          const uint64_t da = make_smem_desc_sw128(smem_u32(xbuf + kb * kFcPanelBytes));
           const uint64_t db = make_smem_desc_sw128(smem_u32(wbuf + s * kFcStageBytes));
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                      (!fresh || (kb | k) != 0) ? 1u : 0u);
+            umma_bf16(acc1, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&w_empty[s]);
+        }
+      };
+      // hidden chunk: 128 x 128 x 256, A = xbuf (tu), B = two stages of two 128 x 64 boxes -> accumulator b
+      auto gemm1 = [&](uint32_t b) {
+        for (int s2 = 0; s2 < 2; ++s2, ++ws) {
+          const int s = ws % kFcStages;
+          mbar_wait(&w_full[s], (ws / kFcStages) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint64_t da = make_smem_desc_sw128(smem_u32(xbuf + (2 * s2 + j) * kFcPanelBytes));
+            const uint64_t db = make_smem_desc_sw128(smem_u32(wbuf + s * kFcStageBytes + j * kFcPanelBytes));
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16(acc1 + b * kFcHC, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc_h,
+                        (s2 | j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&w_empty[s]);
+        }
+      };
+      // y += h_c W2[:, c]^T: 128 x 256 x 128, A = h buffer b, B = two stages
+      auto gemm2 = [&](uint32_t b, bool fresh) {
+        for (int j = 0; j < 2; ++j, ++ws) {
+          const int s = ws % kFcStages;
+          mbar_wait(&w_full[s], (ws / kFcStages) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_smem_desc_sw128(smem_u32(hbuf + b * kFcHBytes + j * kFcPanelBytes));
+          const uint64_t db = make_smem_desc_sw128(smem_u32(wbuf + s * kFcStageBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16(acc2, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                      (!fresh || (j | k) != 0) ? 1u : 0u);
           umma_commit(&w_empty[s]);
         }
       };
       for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
         mbar_wait(x_full, it & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        gemm(xbuf, acc1, true);                          // t2
-        umma_commit(acc1_full);
+        gemm0();                                         // t2
+        umma_commit(g0_full);
         mbar_wait(tu_ready, it & 1);                     // LayerNorm2 wrote tu into xbuf, acc1 is free
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        gemm1(hc & 1);                                   // hidden chunk 0
+        umma_commit(&a1_full[hc & 1]);
         for (int c = 0; c < NCH; ++c, ++hc) {
-          gemm(xbuf, acc1, true);                        // hidden chunk c
-          umma_commit(acc1_full);
-          if (c == NCH - 1) umma_commit(x_free);
-          mbar_wait(h_ready, hc & 1);                    // relu(h_c) is in hbuf, acc1 is free
+          if (c + 1 < NCH) {
+            // chunk c+1 into the other accumulator while the epilogue warps work on chunk c (its previous
+            // reader, chunk c-1, was waited for below one iteration ago)
+            gemm1((hc + 1) & 1);
+            umma_commit(&a1_full[(hc + 1) & 1]);
+            if (c + 1 == NCH - 1) umma_commit(x_free);   // the last GEMM that reads xbuf
+          }
+          mbar_wait(&h_ready[hc & 1], (hc >> 1) & 1);    // relu(h_c) is in its h buffer, its accumulator is free
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (c == 0 && it > 0) {
             mbar_wait(acc2_free, (it - 1) & 1);          // previous tile's LayerNorm3 has drained acc2
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
-          gemm(hbuf, acc2, c == 0);                      // y += h_c W2[:, c]^T
-          umma_commit(h_free);
+          gemm2(hc & 1, c == 0);                         // y += h_c W2[:, c]^T
+          umma_commit(&h_free[hc & 1]);
         }
         umma_commit(acc2_full);
       }
@@ -282,14 +344,14 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int r = q * 32 + lane;                          // row inside the tile
     const int pair_id = 1 + q;
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
-    uint32_t it = 0, a1 = 0, hc = 0;
+    uint32_t it = 0, hc = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
       const int row = mt * kBlockM + r;
       const bool row_ok = row < p.M;
       const float* trow = p.tgt + static_cast<int64_t>(row) * kFcD;
       float* orow = p.out + static_cast<int64_t>(row) * kFcD;
       // ---- LayerNorm2(tgt + t2): x = acc1 + bfu + tgt written back to TMEM, then normalised
-      mbar_wait(acc1_full, a1 & 1); ++a1;
+      mbar_wait(g0_full, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float s_, ss_;
       tmem_add_residual<true>(acc1 + lane_sel, half, p.b_fu, trow, row_ok, s_, ss_);
@@ -306,32 +368,34 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tu_ready);
-      // ---- hidden chunks: relu(acc1 + b1) -> hbuf
+      // ---- hidden chunks: relu(accumulator b + b1) -> h buffer b; this warp: 32 rows x 64 of the 128 columns
       for (int c = 0; c < NCH; ++c, ++hc) {
-        mbar_wait(acc1_full, a1 & 1); ++a1;
-        if (hc > 0) mbar_wait(h_free, (hc - 1) & 1);      // the previous y GEMM has read hbuf
+        const uint32_t b = hc & 1u, use = hc >> 1;
+        mbar_wait(&a1_full[b], use & 1);
+        if (use > 0) mbar_wait(&h_free[b], (use - 1) & 1);       // the y GEMM of two chunks ago has read this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint8_t* hb = hbuf + b * kFcHBytes;
 #pragma unroll 1
-        for (int cc = 0; cc < 8; ++cc) {
-          const int col = half * 128 + cc * 16;
+        for (int cc = 0; cc < 4; ++cc) {
+          const int col = half * 64 + cc * 16;
           uint32_t u[16];
-          tmem_ld16(acc1 + lane_sel + col, u);
+          tmem_ld16(acc1 + b * kFcHC + lane_sel + col, u);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b1 + c * 256 + col + i));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b1 + c * kFcHC + col + i));
             v[i + 0] = fmaxf(__uint_as_float(u[i + 0]) + b4.x, 0.f);
             v[i + 1] = fmaxf(__uint_as_float(u[i + 1]) + b4.y, 0.f);
             v[i + 2] = fmaxf(__uint_as_float(u[i + 2]) + b4.z, 0.f);
             v[i + 3] = fmaxf(__uint_as_float(u[i + 3]) + b4.w, 0.f);
           }
-          store_act16(hbuf, r, col, v);
+          store_act16(hb, r, col, v);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(h_ready);
+        if (lane == 0) mbar_arrive(&h_ready[b]);
       }
       // ---- LayerNorm3(tu + y + b2)
       mbar_wait(acc2_full, it & 1);
@@ -377,7 +441,7 @@ extern "C" int mvg_ffn_chain(const void* aver_bf16, const float* tgt, const void
   if (rc) return rc;
   rc = make_tmap(&tfu, w_fu, kFcD, kFcD, 256);
   if (rc) return rc;
-  rc = make_tmap(&tw1, w1, d_ffn, kFcD, 256);
+  rc = make_tmap(&tw1, w1, d_ffn, kFcD, kFcHC);
   if (rc) return rc;
   rc = make_tmap(&tw2, w2, kFcD, d_ffn, 256);
   if (rc) return rc;
@@ -390,7 +454,7 @@ extern "C" int mvg_ffn_chain(const void* aver_bf16, const float* tgt, const void
     }
     attr_set = true;
   }
-  FfnChainParams p{tgt, b_fu, g2, e2, b1, b2, g3, e3, out, static_cast<int>(M), d_ffn / 256, eps2, eps3};
+  FfnChainParams p{tgt, b_fu, g2, e2, b1, b2, g3, e3, out, static_cast<int>(M), d_ffn / kFcHC, eps2, eps3};
   const int m_tiles = static_cast<int>((M + kBlockM - 1) / kBlockM);
   const int grid = m_tiles < kNumSMs ? m_tiles : kNumSMs;
   ffn_chain_kernel<<<grid, kFcThreads, kFcSmemBytes, static_cast<cudaStream_t>(stream)>>>(tx, tfu, tw1, tw2, p);
