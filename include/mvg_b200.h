@@ -186,6 +186,16 @@ MVG_API int mvg_project_sample_fused(const float* ref3d, const float* cams, cons
                              float* ref2d, uint8_t* bounding, const float* refl_in,
                              void* workspace, void* stream);
 
+/* The two halves of mvg_project_sample_fused as separate calls on the same workspace, so that a host can run
+ * the first on a side stream while the per-point projection GEMM (qproj) is still being computed:
+ *   mvg_project_bin     projection (or `refl_in`), ref2d / bounding, zero rows for out-of-view points, binning
+ *   mvg_sample_gather   per-sample parameters + the tiled gather (needs qproj, value_hm, gmap)
+ * mvg_project_sample_fused == mvg_project_bin followed by mvg_sample_gather on one stream. */
+MVG_API int mvg_project_bin(const float* ref3d, const float* cams, const MvgSampleParams* prm, void* sampled,
+                    float* ref2d, uint8_t* bounding, const float* refl_in, void* workspace, void* stream);
+MVG_API int mvg_sample_gather(const void* value_hm, const void* gmap, const float* qproj, const MvgSampleParams* prm,
+                      void* sampled, const float* ref2d, const float* refl_in, void* workspace, void* stream);
+
 /* The projection (a3) alone - DQDecoderLayer.project_ref_points (dq_decoder.py:331-397) for all V views in
  * one launch, same arithmetic as inside mvg_project_sample_fused (`bounding` bit-exact): ref3d (B,N,3)
  * world mm, cams (B,V,MVG_CAM_FLOATS) -> ref2d (B,V,N,2) fp32 normalised network-image coordinates,

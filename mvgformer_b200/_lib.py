@@ -19,7 +19,7 @@ MVG_F32, MVG_BF16, MVG_F64, MVG_F16 = 0, 1, 2, 3
 MVG_CAM_FIELDS = 11
 MVG_MAX_LEVELS = 4
 MVG_CAM_FLOATS = 64
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class MvgError(RuntimeError):
@@ -64,6 +64,8 @@ SIGNATURES = {
     "mvg_pyramid_to_channels_last": [_P, _I, _I, _P, _I, _I, _P, _P],
     "mvg_linear_bf16": [_P, _P, _P, _P, _I, _L, _I, _I, _L, _I, _P, _P],
     "mvg_project_sample_fused": [_P, _P, _P, _P, _P, C.POINTER(MvgSampleParams), _P, _P, _P, _P, _P, _P],
+    "mvg_project_bin": [_P, _P, C.POINTER(MvgSampleParams), _P, _P, _P, _P, _P, _P],
+    "mvg_sample_gather": [_P, _P, _P, C.POINTER(MvgSampleParams), _P, _P, _P, _P, _P],
     "mvg_project_points": [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P],
     "mvg_value_proj_gemm": [_P, _P, _P, _L, _I, _P, _P, _P],
     "mvg_select_pad": [_P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],

@@ -16,5 +16,5 @@ void set_error(const char* fmt, ...) {
 }  // namespace mvg
 
 extern "C" const char* mvg_last_error(void) { return mvg::t_err; }
-extern "C" int mvg_abi_version(void) { return 9; }
+extern "C" int mvg_abi_version(void) { return 10; }
 extern "C" int64_t mvg_launch_count(void) { return mvg::g_launches.load(); }

@@ -993,74 +993,121 @@ extern "C" int64_t mvg_project_sample_workspace_bytes(const MvgSampleParams* prm
   return make_ws(*prm, nullptr, &w);
 }
 
-extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, const void* value_hm,
-                                        const void* gmap, const float* qproj, const MvgSampleParams* prm,
-                                        void* sampled, float* ref2d, uint8_t* bounding,
-                                        const float* refl_in, void* workspace, void* stream) {
-  using namespace mvg;
-  MVG_REQUIRE(value_hm && gmap && qproj && prm && sampled && workspace, "mvg_project_sample_fused: null pointer");
-  MVG_REQUIRE((reinterpret_cast<uintptr_t>(value_hm) & 15) == 0 && (reinterpret_cast<uintptr_t>(gmap) & 15) == 0,
-              "mvg_project_sample_fused: value / G map must be 16-byte aligned");
-  MVG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
-              "mvg_project_sample_fused: workspace must be 256-byte aligned");
-  MVG_REQUIRE(refl_in || (ref3d && cams && ref2d && bounding),
-              "mvg_project_sample_fused: projection inputs/outputs missing");
-  MVG_REQUIRE(prm->num_levels >= 1 && prm->num_levels <= MVG_MAX_LEVELS,
-              "mvg_project_sample_fused: num_levels %d out of range", prm->num_levels);
-  MVG_REQUIRE(prm->batch > 0 && prm->views > 0 && prm->points > 0, "mvg_project_sample_fused: empty shape");
-  MVG_REQUIRE(prm->ld_g >= 192 && prm->ld_g % 8 == 0, "mvg_project_sample_fused: ld_g %d", prm->ld_g);
+namespace mvg {
+
+// argument checks shared by the three entry points (value_hm / gmap / qproj may be null for the binning half)
+static int check_sample_call(const char* who, const MvgSampleParams* prm, const void* sampled, const void* workspace) {
+  MVG_REQUIRE(prm && sampled && workspace, "%s: null pointer", who);
+  MVG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "%s: workspace must be 256-byte aligned", who);
+  MVG_REQUIRE(prm->num_levels >= 1 && prm->num_levels <= MVG_MAX_LEVELS, "%s: num_levels %d out of range", who,
+              prm->num_levels);
+  MVG_REQUIRE(prm->batch > 0 && prm->views > 0 && prm->points > 0, "%s: empty shape", who);
+  MVG_REQUIRE(prm->ld_g >= 192 && prm->ld_g % 8 == 0, "%s: ld_g %d", who, prm->ld_g);
   MVG_REQUIRE(prm->value_head_stride >= static_cast<int64_t>(prm->batch) * prm->views * prm->spatial_size * 32 &&
                   prm->value_head_stride % 8 == 0,
-              "mvg_project_sample_fused: value_head_stride %lld", static_cast<long long>(prm->value_head_stride));
+              "%s: value_head_stride %lld", who, static_cast<long long>(prm->value_head_stride));
   int s = 0;
   for (int l = 0; l < prm->num_levels; ++l) {
     MVG_REQUIRE(prm->level_h[l] > 1 && prm->level_w[l] > 1 && prm->level_start[l] == s,
-                "mvg_project_sample_fused: level %d shape/start inconsistent", l);
-    MVG_REQUIRE(prm->level_h[l] < 32768 && prm->level_w[l] < 32768,
-                "mvg_project_sample_fused: level %d larger than 32767 texels per side", l);
+                "%s: level %d shape/start inconsistent", who, l);
+    MVG_REQUIRE(prm->level_h[l] < 32768 && prm->level_w[l] < 32768, "%s: level %d larger than 32767 texels per side",
+                who, l);
     s += prm->level_h[l] * prm->level_w[l];
   }
-  MVG_REQUIRE(s == prm->spatial_size, "mvg_project_sample_fused: spatial_size %d != sum H*W %d",
-              prm->spatial_size, s);
-  MVG_REQUIRE(static_cast<int64_t>(s) * 4 < (1ll << 31),
-              "mvg_project_sample_fused: per-view map too large for 32-bit texel offsets");
-  const int64_t total = static_cast<int64_t>(prm->batch) * prm->views * prm->points;
-  MVG_REQUIRE(total < (1ll << 31), "mvg_project_sample_fused: too many items");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MVG_REQUIRE(s == prm->spatial_size, "%s: spatial_size %d != sum H*W %d", who, prm->spatial_size, s);
+  MVG_REQUIRE(static_cast<int64_t>(s) * 4 < (1ll << 31), "%s: per-view map too large for 32-bit texel offsets", who);
+  MVG_REQUIRE(static_cast<int64_t>(prm->batch) * prm->views * prm->points < (1ll << 31), "%s: too many items", who);
+  return MVG_OK;
+}
+
+// projection (or the given per-level reference points) + binning: everything that does not need qproj
+static int run_project_bin(const float* ref3d, const float* cams, const MvgSampleParams* prm, void* sampled,
+                           float* ref2d, uint8_t* bounding, const float* refl_in, void* workspace, cudaStream_t st) {
   GatherWs ws;
   make_ws(*prm, workspace, &ws);
   const int64_t BV = static_cast<int64_t>(prm->batch) * prm->views;
+  const int64_t total = BV * prm->points;
   cudaError_t e = cudaMemsetAsync(ws.counts, 0, static_cast<size_t>(ws.zero_bytes), st);
   if (e != cudaSuccess) {
-    set_error("mvg_project_sample_fused: cudaMemsetAsync: %s", cudaGetErrorString(e));
+    set_error("mvg_project_bin: cudaMemsetAsync: %s", cudaGetErrorString(e));
     return MVG_ELAUNCH;
   }
-  const MvgCamera* cam = reinterpret_cast<const MvgCamera*>(cams);
-  const __half* vhm = static_cast<const __half*>(value_hm);
-  const __half* gmp = static_cast<const __half*>(gmap);
-  __nv_bfloat16* sp = static_cast<__nv_bfloat16*>(sampled);
   const dim3 pc_grid((prm->points + kPcThreads - 1) / kPcThreads, static_cast<unsigned>(BV));
   int rc;
   if (refl_in == nullptr) {
-    project_bin_kernel<<<pc_grid, kPcThreads, 0, st>>>(ref3d, cam, *prm, ref2d, bounding, sp, ws);
-    rc = check_launch("mvg_project_sample_fused(project_bin)");
+    project_bin_kernel<<<pc_grid, kPcThreads, 0, st>>>(ref3d, reinterpret_cast<const MvgCamera*>(cams), *prm, ref2d,
+                                                       bounding, static_cast<__nv_bfloat16*>(sampled), ws);
+    rc = check_launch("mvg_project_bin(project_bin)");
   } else {
     bin_refl_kernel<<<pc_grid, kPcThreads, 0, st>>>(refl_in, *prm, ws);
-    rc = check_launch("mvg_project_sample_fused(bin_refl)");
+    rc = check_launch("mvg_project_bin(bin_refl)");
   }
   if (rc != MVG_OK) return rc;
   bin_scan_kernel<<<1, kScanThreads, 0, st>>>(ws, ws.kx * ws.ky);
-  rc = check_launch("mvg_project_sample_fused(bin_scan)");
+  rc = check_launch("mvg_project_bin(bin_scan)");
   if (rc != MVG_OK) return rc;
   bin_scatter_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(ws);
-  rc = check_launch("mvg_project_sample_fused(bin_scatter)");
-  if (rc != MVG_OK) return rc;
+  return check_launch("mvg_project_bin(bin_scatter)");
+}
+
+static int run_sample_gather(const void* value_hm, const void* gmap, const float* qproj, const MvgSampleParams* prm,
+                             void* sampled, const float* ref2d, const float* refl_in, void* workspace,
+                             cudaStream_t st) {
+  GatherWs ws;
+  make_ws(*prm, workspace, &ws);
+  const __half* vhm = static_cast<const __half*>(value_hm);
+  const __half* gmp = static_cast<const __half*>(gmap);
+  __nv_bfloat16* sp = static_cast<__nv_bfloat16*>(sampled);
   switch (prm->num_levels) {
     case 1: return launch_gather<1>(vhm, gmp, qproj, *prm, sp, ref2d, refl_in, ws, st);
     case 2: return launch_gather<2>(vhm, gmp, qproj, *prm, sp, ref2d, refl_in, ws, st);
     case 3: return launch_gather<3>(vhm, gmp, qproj, *prm, sp, ref2d, refl_in, ws, st);
     default: return launch_gather<4>(vhm, gmp, qproj, *prm, sp, ref2d, refl_in, ws, st);
   }
+}
+
+}  // namespace mvg
+
+extern "C" int mvg_project_bin(const float* ref3d, const float* cams, const MvgSampleParams* prm, void* sampled,
+                               float* ref2d, uint8_t* bounding, const float* refl_in, void* workspace,
+                               void* stream) {
+  using namespace mvg;
+  int rc = check_sample_call("mvg_project_bin", prm, sampled, workspace);
+  if (rc != MVG_OK) return rc;
+  MVG_REQUIRE(refl_in || (ref3d && cams && ref2d && bounding), "mvg_project_bin: projection inputs/outputs missing");
+  return run_project_bin(ref3d, cams, prm, sampled, ref2d, bounding, refl_in, workspace,
+                         static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mvg_sample_gather(const void* value_hm, const void* gmap, const float* qproj,
+                                 const MvgSampleParams* prm, void* sampled, const float* ref2d,
+                                 const float* refl_in, void* workspace, void* stream) {
+  using namespace mvg;
+  int rc = check_sample_call("mvg_sample_gather", prm, sampled, workspace);
+  if (rc != MVG_OK) return rc;
+  MVG_REQUIRE(value_hm && gmap && qproj && (refl_in || ref2d), "mvg_sample_gather: null pointer");
+  MVG_REQUIRE((reinterpret_cast<uintptr_t>(value_hm) & 15) == 0 && (reinterpret_cast<uintptr_t>(gmap) & 15) == 0,
+              "mvg_sample_gather: value / G map must be 16-byte aligned");
+  return run_sample_gather(value_hm, gmap, qproj, prm, sampled, ref2d, refl_in, workspace,
+                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mvg_project_sample_fused(const float* ref3d, const float* cams, const void* value_hm,
+                                        const void* gmap, const float* qproj, const MvgSampleParams* prm,
+                                        void* sampled, float* ref2d, uint8_t* bounding,
+                                        const float* refl_in, void* workspace, void* stream) {
+  using namespace mvg;
+  int rc = check_sample_call("mvg_project_sample_fused", prm, sampled, workspace);
+  if (rc != MVG_OK) return rc;
+  MVG_REQUIRE(value_hm && gmap && qproj, "mvg_project_sample_fused: null pointer");
+  MVG_REQUIRE((reinterpret_cast<uintptr_t>(value_hm) & 15) == 0 && (reinterpret_cast<uintptr_t>(gmap) & 15) == 0,
+              "mvg_project_sample_fused: value / G map must be 16-byte aligned");
+  MVG_REQUIRE(refl_in || (ref3d && cams && ref2d && bounding),
+              "mvg_project_sample_fused: projection inputs/outputs missing");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = run_project_bin(ref3d, cams, prm, sampled, ref2d, bounding, refl_in, workspace, st);
+  if (rc != MVG_OK) return rc;
+  return run_sample_gather(value_hm, gmap, qproj, prm, sampled, ref2d, refl_in, workspace, st);
 }
 
 extern "C" int mvg_project_points(const float* ref3d, const float* cams, int batch, int views, int points,

@@ -250,16 +250,23 @@ class DQDecoderLayer(nn.Module):
         lw = self.packed_weights()
         ref3d = reference_points.detach().reshape(B, N, 3).float().contiguous()
         tgt = tgt.float().contiguous()
+        # 3a. projection + binning (needs only the reference points): on a side stream, under the qproj GEMM
+        value_hm, gmap = ctx.vg_for(self)
+        prm = ops.make_sample_params(B, V, N, ctx.levels, ctx.ld_g, ctx.img_size, ctx.value_head_stride)
+        overlap = not prof.enabled()          # per-stage timing wants the stages back to back on one stream
+        if overlap:
+            binned = ops.project_bin_async(ref3d, ctx.cams, prm)
         # 2. per-point part of the offset / logit projections
         with prof.stage("qproj"):
             qp = None if query_pos is None else query_pos.float().contiguous()
             q_bf = ops.add_cast_bf16(tgt, qp)                                    # with_pos_embed
             qproj = linear(q_bf, pw["w_q"], pw["b_q"], out_dtype=torch.float32)  # (B,N,192)
-        # 3. fused projection + sampling
-        value_hm, gmap = ctx.vg_for(self)
-        prm = ops.make_sample_params(B, V, N, ctx.levels, ctx.ld_g, ctx.img_size, ctx.value_head_stride)
+        # 3b. per-sample parameters + tiled gather
         with prof.stage("project_sample_fused"):
-            sampled, ref2d, bounding, work = ops.project_sample_fused(ref3d, ctx.cams, value_hm, gmap, qproj, prm)
+            if overlap:
+                sampled, ref2d, bounding, work = ops.sample_gather(binned, value_hm, gmap, qproj)
+            else:
+                sampled, ref2d, bounding, work = ops.project_sample_fused(ref3d, ctx.cams, value_hm, gmap, qproj, prm)
         prof.note("inview_items", lambda: work[:B * V].sum())     # evaluated only when profiling is enabled
         # 4. output_proj, mask, view-mean, update MLP, LN, FFN, LN
         with prof.stage("output_proj"):

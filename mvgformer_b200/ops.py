@@ -138,6 +138,59 @@ def project_sample_fused(ref3d: Optional[torch.Tensor], cams: Optional[torch.Ten
     return sampled, ref2d, bounding, work
 
 
+_side_streams = {}
+
+
+class ProjectBin:
+    """The binning half of the fused stage in flight on a side stream (`project_bin_async`)."""
+    __slots__ = ("sampled", "ref2d", "bounding", "work", "prm", "refl", "event")
+
+
+def project_bin_async(ref3d: Optional[torch.Tensor], cams: Optional[torch.Tensor], prm: MvgSampleParams,
+                      refl: Optional[torch.Tensor] = None) -> ProjectBin:
+    """mvg_project_bin (projection + binning: everything of the fused stage that does not need qproj) on a
+    side stream forked from the current one; `sample_gather` joins it.  Between the two calls the caller
+    computes qproj on the current stream, so the ~15 us of small binning kernels overlap the projection GEMM.
+    Works under CUDA-graph capture (the fork / join become graph dependencies)."""
+    lib = _lib.load()
+    dev = (ref3d if ref3d is not None else refl).device
+    B, V, N = prm.batch, prm.views, prm.points
+    pb = ProjectBin()
+    pb.sampled = torch.empty((B, V, N, 256), dtype=torch.bfloat16, device=dev)
+    pb.ref2d = torch.empty((B, V, N, 2), dtype=torch.float32, device=dev)
+    pb.bounding = torch.empty((B, V, N), dtype=torch.uint8, device=dev)
+    nbytes = int(lib.mvg_project_sample_workspace_bytes(C.byref(prm)))
+    if nbytes <= 0:
+        raise _lib.MvgError("mvg_project_sample_workspace_bytes: bad parameters")
+    pb.work = torch.empty(((nbytes + 3) // 4,), dtype=torch.int32, device=dev)
+    pb.prm, pb.refl = prm, refl
+    main = torch.cuda.current_stream(dev)
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        check(lib.mvg_project_bin(_lib.ptr(ref3d), _lib.ptr(cams), C.byref(prm), pb.sampled.data_ptr(),
+                                  pb.ref2d.data_ptr(), pb.bounding.data_ptr(), _lib.ptr(refl), _lib.ptr(pb.work),
+                                  stream_ptr(dev)), "mvg_project_bin")
+        pb.event = side.record_event()
+    return pb
+
+
+def sample_gather(pb: ProjectBin, value_hm: torch.Tensor, gmap: torch.Tensor, qproj: torch.Tensor):
+    """Joins `project_bin_async` and runs mvg_sample_gather on the current stream.
+    -> sampled, ref2d, bounding, work like `project_sample_fused`."""
+    lib = _lib.load()
+    dev = value_hm.device
+    if value_hm.dtype != torch.float16 or gmap.dtype != torch.float16:
+        raise _lib.MvgError("sample_gather: value_hm / gmap must be float16 (ops.value_proj output)")
+    torch.cuda.current_stream(dev).wait_event(pb.event)
+    check(lib.mvg_sample_gather(value_hm.data_ptr(), gmap.data_ptr(), qproj.data_ptr(), C.byref(pb.prm),
+                                pb.sampled.data_ptr(), pb.ref2d.data_ptr(), _lib.ptr(pb.refl), _lib.ptr(pb.work),
+                                stream_ptr(dev)), "mvg_sample_gather")
+    return pb.sampled, pb.ref2d, pb.bounding, pb.work
+
+
 def project_points(ref3d: torch.Tensor, cams: torch.Tensor, img_size) -> Tuple[torch.Tensor, torch.Tensor]:
     """a3 alone: ref3d (B,N,3) fp32 world mm, cams (B,V,64) -> ref2d (B,V,N,2) fp32 normalised
     network-image coordinates, bounding (B,V,N) uint8 (bit-exact with the fused kernel's)."""

@@ -14,6 +14,10 @@ _events: Dict[str, List] = defaultdict(list)
 _notes: Dict[str, List] = defaultdict(list)
 
 
+def enabled() -> bool:
+    return _enabled
+
+
 def enable(flag: bool = True) -> None:
     global _enabled
     _enabled = flag
