@@ -14,10 +14,13 @@
 // Before: three full-size GEMMs (76 800 rows, 0.24 ms per step at Q = 1024) with two bf16 round
 // trips of the hidden activations through HBM and a 16-column padded GEMM for the 3-wide head.
 //
-// One CTA per SM, persistent over the active tiles, 10 warps:
-//   warp 0      TMA producer: 8 weight stages (256 rows x 64 K, 32 KB) per tile
-//   warp 1      TMEM owner + single-thread tcgen05.mma issue (M = 128, N = 256, K = 16)
-//   warps 2-9   row gather into the K-major SWIZZLE_128B A tile, then the two epilogues
+// One CTA per SM, persistent over the active tiles, 14 warps:
+//   warp 0       TMA producer: 8 weight stages (256 rows x 64 K, 32 KB) per tile
+//   warp 1       TMEM owner + single-thread tcgen05.mma issue (M = 128, N = 256, K = 16)
+//   warps 2-9    the two epilogues (h1 -> smem, head)
+//   warps 10-13  row gather of the NEXT tile into the K-major SWIZZLE_128B A tile: xbuf is free as soon as
+//                GEMM 1 has read it, so the gather and GEMM 1 of tile i+1 run under the epilogues of tile i
+//                (with the gather done by the epilogue warps a tile took ~16 us for 2.2 us of MMA)
 #include "tcgen05.cuh"
 
 namespace mvg {
@@ -26,7 +29,8 @@ constexpr int kOcStages = 3;
 constexpr int kOcStageBytes = 256 * kBlockK * 2;        // 32 KB: 256 weight rows x 64 K
 constexpr int kOcPanelBytes = kBlockM * kBlockK * 2;    // 16 KB: 128 rows x 64 K
 constexpr int kOcActBytes = 4 * kOcPanelBytes;          // 64 KB: a 128 x 256 bf16 activation tile
-constexpr int kOcThreads = 10 * 32;
+constexpr int kOcGatherWarps = 4;
+constexpr int kOcThreads = (10 + kOcGatherWarps) * 32;
 constexpr int kOcSmemBytes = 2 * kOcActBytes + kOcStages * kOcStageBytes + 2048 /*partials*/ + 256 /*barriers*/;
 static_assert(kOcSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
@@ -103,7 +107,7 @@ offset_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
     }
-    mbar_init(x_ready, 8);
+    mbar_init(x_ready, kOcGatherWarps);
     mbar_init(x_free, 1);
     mbar_init(acc1_full, 1);
     mbar_init(h_ready, 8);
@@ -171,25 +175,19 @@ offset_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
         umma_commit(acc2_full);
       }
     }
-  } else {
-    // ===================== gather + epilogues (warps 2..9) =====================
-    const int q = warp & 3;                               // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;                     // column half
-    const int r = q * 32 + lane;                          // row inside the tile (epilogues)
-    const int pair_id = 1 + q;
-    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
-    const int te = threadIdx.x - 64;                      // 0..255
-    const int gr = te >> 1, gh = te & 1;                  // gather: row, 128-column half
+  } else if (warp >= 10) {
+    // ===================== row gather (warps 10..13): one row of the tile per thread =====================
+    const int gr = threadIdx.x - 320;                     // 0..127
     uint32_t it = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
-      // ---- gather the tile's rows of attn into the swizzled A tile
-      if (it > 0) mbar_wait(x_free, (it - 1) & 1);        // GEMM 1 of the previous tile has read xbuf
-      {
-        const int64_t row = oc_row_of(static_cast<int64_t>(mt) * kBlockM + gr, n_active, p);
-        const uint4* src = reinterpret_cast<const uint4*>(p.attn + (row < 0 ? 0 : row) * 256 + gh * 128);
+      const int64_t row = oc_row_of(static_cast<int64_t>(mt) * kBlockM + gr, n_active, p);
+      const uint4* src = reinterpret_cast<const uint4*>(p.attn + (row < 0 ? 0 : row) * 256);
+#pragma unroll 1
+      for (int gh = 0; gh < 2; ++gh) {
         uint4 v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = row < 0 ? make_uint4(0u, 0u, 0u, 0u) : __ldg(src + j);
+        for (int j = 0; j < 16; ++j) v[j] = row < 0 ? make_uint4(0u, 0u, 0u, 0u) : __ldg(src + gh * 16 + j);
+        if (gh == 0 && it > 0) mbar_wait(x_free, (it - 1) & 1);     // GEMM 1 of the previous tile has read xbuf
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int col = gh * 128 + j * 8;
@@ -200,6 +198,16 @@ offset_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(x_ready);
+    }
+  } else {
+    // ===================== epilogues (warps 2..9) =====================
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                     // column half
+    const int r = q * 32 + lane;                          // row inside the tile (epilogues)
+    const int pair_id = 1 + q;
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t it = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
       // ---- h1 = relu(acc1 + b1) -> hbuf (bf16).  hbuf is free: this thread waited acc2_full of the previous tile
       mbar_wait(acc1_full, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
