@@ -75,25 +75,61 @@ struct FfnChainParams {
   float eps2, eps3;
 };
 
+// ---- coalesced movement of fp32 tile rows between global memory and the row-per-thread epilogues ----
+// The TMEM layout gives every epilogue thread one row; reading / writing that row straight from / to global
+// memory costs 32 sectors per warp instruction (phase trace of a tile: 18 of 48 us went there).  Instead the
+// four warps of a column half move 128-row x 64-column slabs (32 KB) through a staging area in hbuf (idle
+// during both LayerNorms): the global side is coalesced (16 lanes per 256-byte row piece), the TMEM side is
+// one row per thread, and the 16-byte chunks are XOR-swizzled by the row so that both patterns are free of
+// bank conflicts.
+constexpr int kFcSlabCols = 64;
+constexpr int kFcSlabBytes = kBlockM * kFcSlabCols * 4;          // 32 KB per column half
+static_assert(2 * kFcSlabBytes <= kFcActBytes, "the two staging slabs live in hbuf");
+
+__device__ __forceinline__ uint32_t slab_off(int r, int c) {     // row r, 16-byte chunk c (0..15)
+  return static_cast<uint32_t>(r * 256 + ((c ^ (r & 15)) << 4));
+}
+__device__ __forceinline__ void half_barrier(int half) {         // the four epilogue warps of a column half
+  asm volatile("bar.sync %0, 128;" ::"r"(5 + half) : "memory");
+}
+// global rows [0, rows_valid) x columns [col0, col0 + 64) of the tile starting at `base` -> staging
+template <bool kLdg>
+__device__ __forceinline__ void slab_load(uint8_t* stage, const float* base, int col0, int tid_h, int rows_valid) {
+  const int c = tid_h & 15, r0 = tid_h >> 4;
+  float4 t[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = r0 + i * 8;
+    const float4* src = reinterpret_cast<const float4*>(base + static_cast<int64_t>(r) * kFcD + col0) + c;
+    t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows_valid) t[i] = kLdg ? __ldg(src) : *src;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) *reinterpret_cast<float4*>(stage + slab_off(r0 + i * 8, c)) = t[i];
+}
+__device__ __forceinline__ void slab_store(const uint8_t* stage, float* base, int col0, int tid_h, int rows_valid) {
+  const int c = tid_h & 15, r0 = tid_h >> 4;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = r0 + i * 8;
+    if (r < rows_valid)
+      *(reinterpret_cast<float4*>(base + static_cast<int64_t>(r) * kFcD + col0) + c) =
+          *reinterpret_cast<const float4*>(stage + slab_off(r, c));
+  }
+}
+
 // x = acc + bias + residual for this warp's 128 columns of row r, written back to TMEM; returns the
-// partial sum / sum of squares.  The residual row is fetched 64 columns at a time (16 independent
-// 16-byte loads in flight per thread - a row per thread is an uncoalesced but sector-exact pattern).
+// partial sum / sum of squares.  `res_tile` = the residual tile's row 0 (rows past `rows_valid` read as 0).
 template <bool kLdg>
 __device__ __forceinline__ void tmem_add_residual(uint32_t taddr, int half, const float* __restrict__ bias,
-                                                  const float* res_row, bool row_ok, float& s, float& ss) {
+                                                  const float* res_tile, int rows_valid, uint8_t* stage, int tid_h,
+                                                  int r, float& s, float& ss) {
   s = 0.f; ss = 0.f;
 #pragma unroll 1
   for (int c4 = 0; c4 < 2; ++c4) {
-    const int col0 = half * 128 + c4 * 64;
-    float4 t[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row_ok) {
-        if (kLdg) t[i] = __ldg(reinterpret_cast<const float4*>(res_row + col0) + i);
-        else t[i] = *(reinterpret_cast<const float4*>(res_row + col0) + i);
-      }
-    }
+    const int col0 = half * 128 + c4 * kFcSlabCols;
+    slab_load<kLdg>(stage, res_tile, col0, tid_h, rows_valid);
+    half_barrier(half);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int col = col0 + j * 16;
@@ -103,7 +139,7 @@ __device__ __forceinline__ void tmem_add_residual(uint32_t taddr, int half, cons
 #pragma unroll
       for (int i = 0; i < 16; i += 4) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col + i));
-        const float4 t4 = t[j * 4 + (i >> 2)];
+        const float4 t4 = *reinterpret_cast<const float4*>(stage + slab_off(r, j * 4 + (i >> 2)));
         const float x0 = __uint_as_float(u[i + 0]) + b4.x + t4.x, x1 = __uint_as_float(u[i + 1]) + b4.y + t4.y;
         const float x2 = __uint_as_float(u[i + 2]) + b4.z + t4.z, x3 = __uint_as_float(u[i + 3]) + b4.w + t4.w;
         s += (x0 + x1) + (x2 + x3);
@@ -113,6 +149,7 @@ __device__ __forceinline__ void tmem_add_residual(uint32_t taddr, int half, cons
       }
       tmem_st16(taddr + col, u);
     }
+    half_barrier(half);                                    // slab consumed before the next one overwrites it
   }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -120,12 +157,13 @@ __device__ __forceinline__ void tmem_add_residual(uint32_t taddr, int half, cons
 // LayerNorm over the 256 columns of a row whose pre-norm values sit in TMEM columns
 // [taddr, taddr + 256) of this thread's lane.  `half` selects this warp's 128 columns; the partner
 // warp (same lanes, other half) contributes its partial (sum, sum of squares) through `stats`.
-// Variance = E[x^2] - mean^2 in fp32 (|mean| <~ std for these rows).  fn(col, y[16]) consumes
-// the normalised values.
+// Variance = E[x^2] - mean^2 in fp32 (|mean| <~ std for these rows).  The normalised fp32 rows go to
+// `out_tile` through the staging slab; fn(col, y[16]) sees them as well (bf16 activation tile).
 template <typename F>
 __device__ __forceinline__ void tmem_layernorm(uint32_t taddr, int half, int r, int pair_id, float2* stats,
                                                float s, float ss, const float* __restrict__ gamma,
-                                               const float* __restrict__ beta, float eps, F&& fn) {
+                                               const float* __restrict__ beta, float eps, float* out_tile,
+                                               int rows_valid, uint8_t* stage, int tid_h, F&& fn) {
   stats[half * 128 + r] = make_float2(s, ss);
   pair_barrier(pair_id);
   const float2 o = stats[(half ^ 1) * 128 + r];
@@ -133,23 +171,31 @@ __device__ __forceinline__ void tmem_layernorm(uint32_t taddr, int half, int r, 
   const float mean = (s + o.x) * (1.f / 256.f);
   const float var = fmaxf((ss + o.y) * (1.f / 256.f) - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
+#pragma unroll 1
+  for (int c4 = 0; c4 < 2; ++c4) {
+    const int col0 = half * 128 + c4 * kFcSlabCols;
 #pragma unroll 2
-  for (int cc = 0; cc < 8; ++cc) {
-    const int col = half * 128 + cc * 16;
-    uint32_t u[16];
-    tmem_ld16(taddr + col, u);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    float y[16];
+    for (int j = 0; j < 4; ++j) {
+      const int col = col0 + j * 16;
+      uint32_t u[16];
+      tmem_ld16(taddr + col, u);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float y[16];
 #pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col + i));
-      const float4 e = __ldg(reinterpret_cast<const float4*>(beta + col + i));
-      y[i + 0] = (__uint_as_float(u[i + 0]) - mean) * rstd * g.x + e.x;
-      y[i + 1] = (__uint_as_float(u[i + 1]) - mean) * rstd * g.y + e.y;
-      y[i + 2] = (__uint_as_float(u[i + 2]) - mean) * rstd * g.z + e.z;
-      y[i + 3] = (__uint_as_float(u[i + 3]) - mean) * rstd * g.w + e.w;
+      for (int i = 0; i < 16; i += 4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col + i));
+        const float4 e = __ldg(reinterpret_cast<const float4*>(beta + col + i));
+        y[i + 0] = (__uint_as_float(u[i + 0]) - mean) * rstd * g.x + e.x;
+        y[i + 1] = (__uint_as_float(u[i + 1]) - mean) * rstd * g.y + e.y;
+        y[i + 2] = (__uint_as_float(u[i + 2]) - mean) * rstd * g.z + e.z;
+        y[i + 3] = (__uint_as_float(u[i + 3]) - mean) * rstd * g.w + e.w;
+        *reinterpret_cast<float4*>(stage + slab_off(r, j * 4 + (i >> 2))) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+      }
+      fn(col, y);
     }
-    fn(col, y);
+    half_barrier(half);
+    slab_store(stage, out_tile, col0, tid_h, rows_valid);
+    half_barrier(half);                                    // slab written out before the next one overwrites it
   }
 }
 
@@ -344,26 +390,20 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int r = q * 32 + lane;                          // row inside the tile
     const int pair_id = 1 + q;
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    const int tid_h = ((warp - 2) & 3) * 32 + lane;       // 0..127 inside the column half's four warps
+    uint8_t* stage = hbuf + half * kFcSlabBytes;          // fp32 slab staging (hbuf is idle during the LayerNorms)
     uint32_t it = 0, hc = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
-      const int row = mt * kBlockM + r;
-      const bool row_ok = row < p.M;
-      const float* trow = p.tgt + static_cast<int64_t>(row) * kFcD;
-      float* orow = p.out + static_cast<int64_t>(row) * kFcD;
+      const int rows_valid = min(kBlockM, p.M - mt * kBlockM);
+      const float* ttile = p.tgt + static_cast<int64_t>(mt) * kBlockM * kFcD;
+      float* otile = p.out + static_cast<int64_t>(mt) * kBlockM * kFcD;
       // ---- LayerNorm2(tgt + t2): x = acc1 + bfu + tgt written back to TMEM, then normalised
       mbar_wait(g0_full, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float s_, ss_;
-      tmem_add_residual<true>(acc1 + lane_sel, half, p.b_fu, trow, row_ok, s_, ss_);
-      tmem_layernorm(acc1 + lane_sel, half, r, pair_id, stats, s_, ss_, p.g2, p.e2, p.eps2,
-                     [&](int col, const float* y) {
-                       if (row_ok) {
-#pragma unroll
-                         for (int i = 0; i < 16; i += 4)
-                           *reinterpret_cast<float4*>(orow + col + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
-                       }
-                       store_act16(xbuf, r, col, y);
-                     });
+      tmem_add_residual<true>(acc1 + lane_sel, half, p.b_fu, ttile, rows_valid, stage, tid_h, r, s_, ss_);
+      tmem_layernorm(acc1 + lane_sel, half, r, pair_id, stats, s_, ss_, p.g2, p.e2, p.eps2, otile, rows_valid,
+                     stage, tid_h, [&](int col, const float* y) { store_act16(xbuf, r, col, y); });
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -400,15 +440,10 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       // ---- LayerNorm3(tu + y + b2)
       mbar_wait(acc2_full, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tmem_add_residual<false>(acc2 + lane_sel, half, p.b2, orow, row_ok, s_, ss_);   // + tu, written by this thread
-      tmem_layernorm(acc2 + lane_sel, half, r, pair_id, stats, s_, ss_, p.g3, p.e3, p.eps3,
-                     [&](int col, const float* y) {
-                       if (row_ok) {
-#pragma unroll
-                         for (int i = 0; i < 16; i += 4)
-                           *reinterpret_cast<float4*>(orow + col + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
-                       }
-                     });
+      // + tu: written to `out` by the LayerNorm2 slab stores of this column half (ordered by half_barrier)
+      tmem_add_residual<false>(acc2 + lane_sel, half, p.b2, otile, rows_valid, stage, tid_h, r, s_, ss_);
+      tmem_layernorm(acc2 + lane_sel, half, r, pair_id, stats, s_, ss_, p.g3, p.e3, p.eps3, otile, rows_valid,
+                     stage, tid_h, [&](int, const float*) {});
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(acc2_free);

@@ -11,7 +11,7 @@ bld=$src/build_$name
 mkdir -p $out $bld
 flags="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr"
 for f in api deform_forward deform_backward pyramid project_sample select_pad offsets_dlt elementwise linear_tcgen05 pre_post ffn_chain cameras decoder_driver offset_chain; do
-  if [ "$f" = "project_sample" ] || [ ! -f $src/build/$f.o ]; then
+  if [ "$f" = "project_sample" ] || [ "$f" = "${VARIANT_SRC:-project_sample}" ] || [ ! -f $src/build/$f.o ]; then
     nvcc $flags $extra -c ${PS_SRC:-$src/$f.cu} -o $bld/$f.o &
   else
     cp $src/build/$f.o $bld/$f.o
