@@ -60,6 +60,21 @@ __device__ __forceinline__ void store_act16(uint8_t* act, int r, int col, const 
   }
 }
 
+#ifdef MVG_FFN_TRACE    // phase timestamps of CTA 0 (debug builds: VARIANT_SRC=ffn_chain tools/build_variant.sh trace -DMVG_FFN_TRACE,
+                        // read with tools/trace_ffn.py)
+__device__ unsigned long long g_ffn_trace[64];
+__device__ __forceinline__ void ffn_stamp(int slot) {
+  if (blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_ffn_trace[slot] = t;
+  }
+}
+#define FFN_STAMP(slot) ffn_stamp(slot)
+#else
+#define FFN_STAMP(slot)
+#endif
+
 struct FfnChainParams {
   const float* tgt;        // (M, 256) fp32
   const float* b_fu;       // (256)
@@ -208,6 +223,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  if (threadIdx.x == 0) FFN_STAMP(41);
   uint8_t* xbuf = smem;                                  // aver tile, then tu (bf16)
   uint8_t* hbuf = smem + kFcActBytes;                    // relu(hidden chunk) (bf16)
   uint8_t* wbuf = smem + 2 * kFcActBytes;                // weight ring
@@ -263,6 +279,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc1 = tmem_base, acc2 = tmem_base + 256;
+  if (threadIdx.x == 0) FFN_STAMP(40);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -355,11 +372,15 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
       };
       for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+        FFN_STAMP(0);
         mbar_wait(x_full, it & 1);
+        FFN_STAMP(1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         gemm0();                                         // t2
         umma_commit(g0_full);
+        FFN_STAMP(2);
         mbar_wait(tu_ready, it & 1);                     // LayerNorm2 wrote tu into xbuf, acc1 is free
+        FFN_STAMP(3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         gemm1(hc & 1);                                   // hidden chunk 0
         umma_commit(&a1_full[hc & 1]);
@@ -372,6 +393,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (c + 1 == NCH - 1) umma_commit(x_free);   // the last GEMM that reads xbuf
           }
           mbar_wait(&h_ready[hc & 1], (hc >> 1) & 1);    // relu(h_c) is in its h buffer, its accumulator is free
+          FFN_STAMP(4 + (c & 7));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (c == 0 && it > 0) {
             mbar_wait(acc2_free, (it - 1) & 1);          // previous tile's LayerNorm3 has drained acc2
@@ -381,6 +403,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           umma_commit(&h_free[hc & 1]);
         }
         umma_commit(acc2_full);
+        FFN_STAMP(12);
       }
     }
   } else {
@@ -399,20 +422,24 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       float* otile = p.out + static_cast<int64_t>(mt) * kBlockM * kFcD;
       // ---- LayerNorm2(tgt + t2): x = acc1 + bfu + tgt written back to TMEM, then normalised
       mbar_wait(g0_full, it & 1);
+      if (warp == 2 && lane == 0) FFN_STAMP(16);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float s_, ss_;
       tmem_add_residual<true>(acc1 + lane_sel, half, p.b_fu, ttile, rows_valid, stage, tid_h, r, s_, ss_);
+      if (warp == 2 && lane == 0) FFN_STAMP(17);
       tmem_layernorm(acc1 + lane_sel, half, r, pair_id, stats, s_, ss_, p.g2, p.e2, p.eps2, otile, rows_valid,
                      stage, tid_h, [&](int col, const float* y) { store_act16(xbuf, r, col, y); });
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tu_ready);
+      if (warp == 2 && lane == 0) FFN_STAMP(18);
       // ---- hidden chunks: relu(accumulator b + b1) -> h buffer b; this warp: 32 rows x 64 of the 128 columns
       for (int c = 0; c < NCH; ++c, ++hc) {
         const uint32_t b = hc & 1u, use = hc >> 1;
         mbar_wait(&a1_full[b], use & 1);
         if (use > 0) mbar_wait(&h_free[b], (use - 1) & 1);       // the y GEMM of two chunks ago has read this buffer
+        if (warp == 2 && lane == 0) FFN_STAMP(20 + (c & 7));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint8_t* hb = hbuf + b * kFcHBytes;
 #pragma unroll 1
@@ -431,14 +458,19 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             v[i + 3] = fmaxf(__uint_as_float(u[i + 3]) + b4.w, 0.f);
           }
           store_act16(hb, r, col, v);
+          if (warp == 2 && lane == 0 && c == 3) FFN_STAMP(49 + cc);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (warp == 2 && lane == 0 && c == 3) FFN_STAMP(53);
         __syncwarp();
         if (lane == 0) mbar_arrive(&h_ready[b]);
+        if (warp == 2 && lane == 0 && c == 3) FFN_STAMP(54);
       }
       // ---- LayerNorm3(tu + y + b2)
+      if (warp == 2 && lane == 0) FFN_STAMP(29);
       mbar_wait(acc2_full, it & 1);
+      if (warp == 2 && lane == 0) FFN_STAMP(30);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // + tu: written to `out` by the LayerNorm2 slab stores of this column half (ordered by half_barrier)
       tmem_add_residual<false>(acc2 + lane_sel, half, p.b2, otile, rows_valid, stage, tid_h, r, s_, ss_);
@@ -447,6 +479,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(acc2_free);
+      if (warp == 2 && lane == 0) FFN_STAMP(31);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -495,3 +528,9 @@ extern "C" int mvg_ffn_chain(const void* aver_bf16, const float* tgt, const void
   ffn_chain_kernel<<<grid, kFcThreads, kFcSmemBytes, static_cast<cudaStream_t>(stream)>>>(tx, tfu, tw1, tw2, p);
   return check_launch("mvg_ffn_chain");
 }
+
+#ifdef MVG_FFN_TRACE
+extern "C" __attribute__((visibility("default"))) int mvg_debug_ffn_trace(unsigned long long* out64) {
+  return cudaMemcpyFromSymbol(out64, mvg::g_ffn_trace, sizeof(unsigned long long) * 64) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -31,5 +31,9 @@ names = {41: "kernel entry", 40: "after barrier init + TMEM alloc", 0: "MMA: loo
 for c in range(8):
     names[4 + c] = f"MMA: h_ready chunk {c}"
     names[20 + c] = f"EPI: chunk {c} accumulator ready"
+for k in range(4):
+    names[49 + k] = f"EPI:   chunk 3, 16 columns #{k} stored"
+names[53] = "EPI:   chunk 3 fences done"
+names[54] = "EPI:   chunk 3 arrived"
 for slot, t in sorted(((s, buf[s]) for s in names if buf[s]), key=lambda x: x[1]):
     print(f"{(t - t0) / 1e3:8.2f} us  {names[slot]}")
