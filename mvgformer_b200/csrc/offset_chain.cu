@@ -209,24 +209,36 @@ offset_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
     uint32_t it = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
       // ---- h1 = relu(acc1 + b1) -> hbuf (bf16).  hbuf is free: this thread waited acc2_full of the previous tile
+      // The per-column vectors are fetched in batches ahead of the TMEM reads: read 16 bytes at a time right
+      // before use, every group of 16 columns paid an L2 round trip (phase trace of ffn_chain: 0.29 of 0.35 us).
+      float4 bb[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) bb[i] = __ldg(reinterpret_cast<const float4*>(p.b1 + half * 128) + i);
       mbar_wait(acc1_full, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int cc = 0; cc < 8; ++cc) {
-        const int col = half * 128 + cc * 16;
-        uint32_t u[16];
-        tmem_ld16(acc1 + lane_sel + col, u);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float v[16];
+      for (int c4 = 0; c4 < 2; ++c4) {
+        if (c4 == 1) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b1 + col + i));
-          v[i + 0] = fmaxf(__uint_as_float(u[i + 0]) + b4.x, 0.f);
-          v[i + 1] = fmaxf(__uint_as_float(u[i + 1]) + b4.y, 0.f);
-          v[i + 2] = fmaxf(__uint_as_float(u[i + 2]) + b4.z, 0.f);
-          v[i + 3] = fmaxf(__uint_as_float(u[i + 3]) + b4.w, 0.f);
+          for (int i = 0; i < 16; ++i) bb[i] = __ldg(reinterpret_cast<const float4*>(p.b1 + half * 128 + 64) + i);
         }
-        oc_store_act16(hbuf, r, col, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = half * 128 + c4 * 64 + j * 16;
+          uint32_t u[16];
+          tmem_ld16(acc1 + lane_sel + col, u);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = bb[j * 4 + (i >> 2)];
+            v[i + 0] = fmaxf(__uint_as_float(u[i + 0]) + b4.x, 0.f);
+            v[i + 1] = fmaxf(__uint_as_float(u[i + 1]) + b4.y, 0.f);
+            v[i + 2] = fmaxf(__uint_as_float(u[i + 2]) + b4.z, 0.f);
+            v[i + 3] = fmaxf(__uint_as_float(u[i + 3]) + b4.w, 0.f);
+          }
+          oc_store_act16(hbuf, r, col, v);
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -236,18 +248,26 @@ offset_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
       mbar_wait(acc2_full, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-#pragma unroll 1
+#pragma unroll 2
       for (int cc = 0; cc < 8; ++cc) {
         const int col = half * 128 + cc * 16;
+        float4 vb[4], va[4], vw[4], vc[4];                  // b2 and the three rows of W3 for this group: 16 loads in flight
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          vb[i] = __ldg(reinterpret_cast<const float4*>(p.b2 + col) + i);
+          va[i] = __ldg(reinterpret_cast<const float4*>(p.w3 + col) + i);
+          vw[i] = __ldg(reinterpret_cast<const float4*>(p.w3 + 256 + col) + i);
+          vc[i] = __ldg(reinterpret_cast<const float4*>(p.w3 + 512 + col) + i);
+        }
         uint32_t u[16];
         tmem_ld16(acc2 + lane_sel + col, u);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + col + i));
-          const float4 wa = __ldg(reinterpret_cast<const float4*>(p.w3 + col + i));
-          const float4 wb = __ldg(reinterpret_cast<const float4*>(p.w3 + 256 + col + i));
-          const float4 wc = __ldg(reinterpret_cast<const float4*>(p.w3 + 512 + col + i));
+          const float4 b4 = vb[i >> 2];
+          const float4 wa = va[i >> 2];
+          const float4 wb = vw[i >> 2];
+          const float4 wc = vc[i >> 2];
           const float h0 = fmaxf(__uint_as_float(u[i + 0]) + b4.x, 0.f), h1 = fmaxf(__uint_as_float(u[i + 1]) + b4.y, 0.f);
           const float h2 = fmaxf(__uint_as_float(u[i + 2]) + b4.z, 0.f), h3 = fmaxf(__uint_as_float(u[i + 3]) + b4.w, 0.f);
           o0 += h0 * wa.x + h1 * wa.y + h2 * wa.z + h3 * wa.w;
