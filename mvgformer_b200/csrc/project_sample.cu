@@ -610,6 +610,22 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
   }
 }
 
+#ifdef MVG_GT_TRACE     // phase timestamps of CTA 0, units 6..9 (debug builds: tools/build_variant.sh gtrace -DMVG_GT_TRACE,
+                        // read with tools/trace_gather.py).  Slot = (unit - 6) * 32 + event.
+__device__ unsigned long long g_gt_trace[160];
+__device__ int g_gt_trace_count[4];
+__device__ __forceinline__ void gt_stamp(uint32_t seq, int ev) {
+  if (blockIdx.x == 0 && seq >= 6 && seq < 10) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_gt_trace[(seq - 6) * 32 + ev] = t;
+  }
+}
+#define GT_STAMP(seq, ev) gt_stamp(seq, ev)
+#else
+#define GT_STAMP(seq, ev)
+#endif
+
 // ------------------------------------------------------------------ the gather proper
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -799,7 +815,9 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
         if (lane == 0) ws.direct_list[atomicAdd(ws.ctrs + 3, 1)] = unit;      // left to gather_direct_kernel
       }
       const uint32_t par = seq & 1u;
+      if (lane == 0) GT_STAMP(seq, 0);
       mbar_wait(&empty[0], par ^ 1u);      // level 0 of unit seq-1 consumed => descriptor slot (seq & 1) is free
+      if (lane == 0) GT_STAMP(seq, 1);
       UnitDesc* d = &sdesc[par];
       if (unit < 0) {
         if (lane == 0) { d->count = -1; mbar_arrive(&full[0]); }
@@ -820,6 +838,7 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
 #pragma unroll
       for (int l = 0; l < LV; ++l) {
         if (l > 0) mbar_wait(&empty[l], par ^ 1u);
+        if (lane == 0) GT_STAMP(seq, 2 + 2 * l);
         const int bw = box[l].z, bh = box[l].w;
         const uint32_t row_bytes = static_cast<uint32_t>(bw) * 64u;
         const uint32_t rec_bytes = static_cast<uint32_t>(count) * kRecBytes;
@@ -837,6 +856,8 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
         for (int r = lane; r < bh_eff; r += 32)
           bulk_g2s(region[l] + static_cast<uint32_t>(r) * row_bytes, src0 + static_cast<int64_t>(r) * prm.level_w[l] * 32,
                    row_bytes, &full[l]);
+        __syncwarp();
+        if (lane == 0) GT_STAMP(seq, 3 + 2 * l);
       }
       ++seq;
     }
@@ -848,7 +869,9 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
     const uint32_t rec_lane = static_cast<uint32_t>(dx * 64 + q * 16);
     for (;;) {
       const uint32_t par = seq & 1u;
+      if (warp == 0 && lane == 0) GT_STAMP(seq, 15);
       mbar_wait(&full[0], par);
+      if (warp == 0 && lane == 0) GT_STAMP(seq, 16);
       const UnitDesc* d = &sdesc[par];
       const int count = d->count;
       if (count < 0) break;
@@ -864,6 +887,7 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
 #pragma unroll
       for (int l = 0; l < LV; ++l) {
         if (l > 0) mbar_wait(&full[l], par);
+        if (warp == 0 && lane == 0) GT_STAMP(seq, 17 + 3 * l);
         const int4 box = d->box[l];
         const uint32_t tile = region[l] + static_cast<uint32_t>(lane & 7) * 16u -
                               static_cast<uint32_t>(box.y * box.z + box.x) * 64u;
@@ -891,16 +915,24 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
           }
         }
         __syncwarp();
+        if (warp == 0 && lane == 0) GT_STAMP(seq, 18 + 3 * l);
         if (lane == 0) mbar_arrive(&empty[l]);
       }
+#ifdef MVG_GT_TRACE
+      if (warp == 0 && lane == 0) { GT_STAMP(seq, 27); if (blockIdx.x == 0 && seq >= 6 && seq < 10) g_gt_trace_count[seq - 6] = count; }
+#endif
+      // role reduction of all kIPW slots without branches (a missing item's accumulators are zero): the
+      // independent shuffle chains overlap, only the store is predicated.  With one branchy block per item
+      // this epilogue took 1.5 us of a 4.7 us unit (phase trace, tools/trace_gather.py).
+      float vred[kIPW];
+#pragma unroll
+      for (int k = 0; k < kIPW; ++k) vred[k] = reduce_roles(acc[k][0], acc[k][1], acc[k][2], acc[k][3], lane);
 #pragma unroll
       for (int k = 0; k < kIPW; ++k) {
-        if (warp + kGWarps * k < count) {
-          const float v = reduce_roles(acc[k][0], acc[k][1], acc[k][2], acc[k][3], lane);
-          const int64_t item = __shfl_sync(0xffffffffu, my_item, k);
-          sampled[item * 256 + head * 32 + chn] = __float2bfloat16(v);
-        }
+        const int64_t item = __shfl_sync(0xffffffffu, my_item, k);
+        if (warp + kGWarps * k < count) sampled[item * 256 + head * 32 + chn] = __float2bfloat16(vred[k]);
       }
+      if (warp == 0 && lane == 0) GT_STAMP(seq, 28);
       ++seq;
     }
   }
@@ -1121,3 +1153,10 @@ extern "C" int mvg_project_points(const float* ref3d, const float* cams, int bat
       ref3d, reinterpret_cast<const MvgCamera*>(cams), views, points, img_w, img_h, ref2d, bounding);
   return check_launch("mvg_project_points");
 }
+
+#ifdef MVG_GT_TRACE
+extern "C" __attribute__((visibility("default"))) int mvg_debug_gather_trace(unsigned long long* out160, int* counts4) {
+  if (cudaMemcpyFromSymbol(out160, mvg::g_gt_trace, sizeof(unsigned long long) * 160) != cudaSuccess) return -1;
+  return cudaMemcpyFromSymbol(counts4, mvg::g_gt_trace_count, sizeof(int) * 4) == cudaSuccess ? 0 : -1;
+}
+#endif
