@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true", help="skip the CUDA-vs-oracle parity block (one oracle decoder pass)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--e2e-ablate", default=None, choices=[None, "copy", "compute", "d2h"],
+                    help="diagnostic: drop the H2D copies / the decoder replay / the host-side consume from the "
+                         "e2e loop (the line is marked and is not a bench value)")
     ap.add_argument("--pipeline", default="auto", choices=["auto", "on", "off"],
                     help="overlap the query-independent prologue of step i+1 with the layers of step i "
                          "(graphs.PipelinedDecoder); auto = on for N > 1")
@@ -461,7 +464,7 @@ def run_ours(a):
                     if world > 1:
                         exch[b_].upload_shard(host_feats)
                         exch[b_].allgather()
-                    else:
+                    elif a.e2e_ablate != "copy":
                         for dst, src in zip(g_.s_feats, host_feats):
                             dst.copy_(src, non_blocking=True)
                     h2d_done[b_].record(copy_stream)
@@ -474,12 +477,12 @@ def run_ours(a):
                     else:
                         qi(B, out=(g_.s_tgt, g_.s_qpos, g_.s_ref))
                 main.wait_event(h2d_done[b_])
-                out = g_.replay()
+                out = g_.replay() if a.e2e_ablate != "compute" else g_.out
                 out_pose[b_].copy_(out[0], non_blocking=True)
                 out_prob[b_].copy_(out[1], non_blocking=True)
                 compute_done[b_].record(main)
                 d2h_done[b_].record(main)
-                if s_ > 0:                                        # consume frame s-1 on the host
+                if s_ > 0 and a.e2e_ablate != "d2h":              # consume frame s-1 on the host
                     d2h_done[b_ ^ 1].synchronize()
                     checksum["v"] += float(out_prob[b_ ^ 1][0, 0, 1])
                 state["step"] = s_ + 1
@@ -535,6 +538,7 @@ def run_ours(a):
                "h2d_bytes_per_step": int(h2d_t.item()),
                "d2h_bytes_per_step": int(out_pose[0].numel() * 4 + out_prob[0].numel() * 4),
                "ms_per_step": e2e_ms / a.steps,
+               **({"ablate": a.e2e_ablate + " (diagnostic run, not a bench value)"} if a.e2e_ablate else {}),
                "inputs": "pyramid from pinned host memory (whole job: every byte crosses PCIe once"
                          + (f", 1/{world} per rank, NCCL all-gather over NVLink for the rest)" if world > 1 else ")")
                          + "; tgt / query_pos / reference points built on the device by mvg_init_queries",

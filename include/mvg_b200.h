@@ -137,6 +137,17 @@ MVG_API int mvg_linear_bf16(const void* A, const void* W, const float* bias, voi
 MVG_API int mvg_value_proj_gemm(const void* feat, const void* W, const float* bias, int64_t M, int layers,
                         void* value_hm, void* gmap, void* stream);
 
+/* The same projection reading the NCHW pyramid levels IN PLACE (what the reference's backbone hands to
+ * ProjAttn before its flatten + permute, projattn.py:160): src_levels = HOST array of num_levels device
+ * pointers to (rows = V*B, 256, H_l, W_l) BF16 maps, level_hw[l] = H_l * W_l.  An M tile of 128 texels is
+ * loaded by TMA as an MN-major tcgen05 operand, so mvg_pyramid_to_channels_last and its (rows, S, 256)
+ * buffer are not needed.  Requires H_l * W_l % 128 == 0 for every level
+ * (mvg_value_proj_gemm_nchw_supported returns 1); results are identical to the two-step path. */
+MVG_API int mvg_value_proj_gemm_nchw_supported(int num_levels, const int* level_hw);
+MVG_API int mvg_value_proj_gemm_nchw(const void* const* src_levels, int num_levels, const int* level_hw, int rows,
+                             const void* W, const float* bias, int layers, void* value_hm, void* gmap,
+                             void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Fused projection + projective attention sampling for all (b, v, n):
  *   a3  project_ref_points   (dq_decoder.py:331-397, cameras.py:167-207, transforms.py:135-141)

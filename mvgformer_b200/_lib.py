@@ -68,6 +68,8 @@ SIGNATURES = {
     "mvg_sample_gather": [_P, _P, _P, C.POINTER(MvgSampleParams), _P, _P, _P, _P, _P],
     "mvg_project_points": [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P],
     "mvg_value_proj_gemm": [_P, _P, _P, _L, _I, _P, _P, _P],
+    "mvg_value_proj_gemm_nchw_supported": [_I, _P],
+    "mvg_value_proj_gemm_nchw": [_P, _I, _P, _I, _P, _P, _I, _P, _P, _P],
     "mvg_select_pad": [_P, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "mvg_offsets_dlt": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P],
     "mvg_triangulate": [_P, _P, _P, _I, _I, _I, _P, _P],

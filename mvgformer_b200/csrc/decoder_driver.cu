@@ -246,15 +246,21 @@ extern "C" int mvg_decoder(const MvgDecoderConfig* cfg, const MvgLayerWeights* l
   const int64_t B = cfg->batch, V = cfg->views, N = static_cast<int64_t>(cfg->queries) * cfg->joints, L = cfg->layers;
   const int64_t rows = V * B * prm.spatial_size;
   const void* feat = pyramid_cl;
-  if (nchw) {
-    int hw[MVG_MAX_LEVELS];
-    for (int l = 0; l < cfg->num_levels; ++l) hw[l] = cfg->level_h[l] * cfg->level_w[l];
-    rc = mvg_pyramid_to_channels_last(pyramid_levels, pyramid_dtype, cfg->num_levels, hw, static_cast<int>(V * B), 256,
-                                      ws.feat_cl, stream);
-    if (rc != MVG_OK) return rc;
-    feat = ws.feat_cl;
+  int hw[MVG_MAX_LEVELS];
+  for (int l = 0; l < cfg->num_levels; ++l) hw[l] = cfg->level_h[l] * cfg->level_w[l];
+  if (nchw && pyramid_dtype == MVG_BF16 && mvg_value_proj_gemm_nchw_supported(cfg->num_levels, hw)) {
+    // bf16 levels of 128-texel multiples: the GEMM reads them in place (MN-major TMA operand)
+    rc = mvg_value_proj_gemm_nchw(pyramid_levels, cfg->num_levels, hw, static_cast<int>(V * B), w_vg_all, b_vg_all,
+                                  cfg->layers, ws.value_hm, ws.gmap, stream);
+  } else {
+    if (nchw) {
+      rc = mvg_pyramid_to_channels_last(pyramid_levels, pyramid_dtype, cfg->num_levels, hw, static_cast<int>(V * B),
+                                        256, ws.feat_cl, stream);
+      if (rc != MVG_OK) return rc;
+      feat = ws.feat_cl;
+    }
+    rc = mvg_value_proj_gemm(feat, w_vg_all, b_vg_all, rows, cfg->layers, ws.value_hm, ws.gmap, stream);
   }
-  rc = mvg_value_proj_gemm(feat, w_vg_all, b_vg_all, rows, cfg->layers, ws.value_hm, ws.gmap, stream);
   if (rc != MVG_OK) return rc;
   const float* tgt_l = tgt;
   const float* ref_l = ref3d;

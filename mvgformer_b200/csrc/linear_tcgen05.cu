@@ -36,9 +36,19 @@ constexpr int kSmemBytesV2 = kMaxWBytes + kStages * kATileBytes + kEpiWarps * kS
 // accumulator is double-buffered in TMEM so the 8 epilogue warps drain tile i while the MMA warp
 // already issues tile i+1.  grid = n_chunks x groups; the CTAs of one group sweep the same M tiles
 // at the same time, so an A tile is read from HBM once and hit in L2 by the other chunks.
+// A operand given as the NCHW pyramid levels themselves (mvg_value_proj_gemm_nchw): per level a 3-D map
+// {s, channel, view-frame row}; an M tile of 128 texels is two {64 s, 64 c} boxes = an MN-major operand, so
+// the channels-last copy of the pyramid (mvg_pyramid_to_channels_last: 206 MB of traffic) is never made.
+struct NchwA {
+  CUtensorMap map[MVG_MAX_LEVELS];
+  int tile_start[MVG_MAX_LEVELS + 1];    // first 128-texel tile of level l inside one view-frame row
+  int num_levels;                        // 0: A is the row-major (M, K) matrix of tmap_a
+  int tiles_per_row;                     // S / 128
+};
+
 template <typename OutT>
 __global__ void __launch_bounds__(kGemmThreadsV2, 1)
-linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a,
+linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ NchwA nchw,
                          const __grid_constant__ CUtensorMap tmap_w,
                          const __grid_constant__ CUtensorMap tmap_out,
                          const __grid_constant__ CUtensorMap tmap_hm, int hm_period, int use_tma_store,
@@ -106,14 +116,26 @@ linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&a_empty[s], ph ^ 1);
           mbar_expect_tx(&a_full[s], kATileBytes);
-          tma_load_2d(&tmap_a, &a_full[s], smem_a + s * kATileBytes, kb * kBlockK, mt * kBlockM);
+          if (nchw.num_levels > 0) {
+            const int row = mt / nchw.tiles_per_row, t = mt % nchw.tiles_per_row;
+            int l = 0;
+            while (l + 1 < nchw.num_levels && t >= nchw.tile_start[l + 1]) ++l;
+            const int s0 = (t - nchw.tile_start[l]) * kBlockM;
+            tma_load_3d(&nchw.map[l], &a_full[s], smem_a + s * kATileBytes, s0, kb * kBlockK, row);
+            tma_load_3d(&nchw.map[l], &a_full[s], smem_a + s * kATileBytes + kATileBytes / 2, s0 + kBlockM / 2,
+                        kb * kBlockK, row);
+          } else {
+            tma_load_2d(&tmap_a, &a_full[s], smem_a + s * kATileBytes, kb * kBlockK, mt * kBlockM);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(NC);
+      const bool a_mn = nchw.num_levels > 0;
+      const uint32_t idesc = make_idesc_bf16(NC, a_mn);
+      const uint64_t a_step = a_mn ? (2048u >> 4) : 2u;   // start-address advance per K=16 step
       mbar_wait(w_full, 0);
       uint32_t it = 0, i = 0;
       for (int mt = group; mt < m_tiles; mt += groups, ++i) {
@@ -126,11 +148,12 @@ linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&a_full[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + s * kATileBytes));
+          const uint32_t a_addr = smem_u32(smem_a + s * kATileBytes);
+          const uint64_t da = a_mn ? make_smem_desc_sw128_mn(a_addr) : make_smem_desc_sw128(a_addr);
           const uint64_t db = make_smem_desc_sw128(smem_u32(smem_w + kb * w_kb_bytes));
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+            umma_bf16(tmem_d, da + a_step * static_cast<uint64_t>(k), db + static_cast<uint64_t>(2 * k),
                       idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&a_empty[s]);
         }
@@ -367,7 +390,7 @@ static int make_hm_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int hea
 template <typename OutT>
 static int launch_linear(const void* A, const void* W, const float* bias, const uint8_t* row_mask,
                          void* out, int64_t M, int Nout, int K, int64_t ldo, int relu,
-                         cudaStream_t st, void* value_hm = nullptr) {
+                         cudaStream_t st, void* value_hm = nullptr, const NchwA* nchw_a = nullptr) {
   // weight chunk width: as wide as fits 128 KB / one UMMA (256), split evenly over the chunks
   int nc_max = kMaxWBytes / (K * 2);
   nc_max = nc_max > 256 ? 256 : (nc_max / 16) * 16;
@@ -390,10 +413,16 @@ static int launch_linear(const void* A, const void* W, const float* bias, const 
   int groups = kNumSMs / n_chunks;
   if (groups > m_tiles) groups = m_tiles;
   CUtensorMap ta, tw;
-  int rc = make_tmap(&ta, A, M, K, kBlockM);
+  int rc = make_tmap(&tw, W, Nout, K, NC);
   if (rc) return rc;
-  rc = make_tmap(&tw, W, Nout, K, NC);
-  if (rc) return rc;
+  static const NchwA kNoNchw{};                      // num_levels = 0: row-major A
+  if (nchw_a == nullptr) {
+    rc = make_tmap(&ta, A, M, K, kBlockM);
+    if (rc) return rc;
+    nchw_a = &kNoNchw;
+  } else {
+    ta = tw;                                         // unused by the kernel
+  }
   CUtensorMap tout, thm;
   int hm_period = 0;
   if (value_hm != nullptr) {
@@ -422,7 +451,7 @@ static int launch_linear(const void* A, const void* W, const float* bias, const 
     attr_set = true;
   }
   kern<<<n_chunks * groups, kGemmThreadsV2, kSmemBytesV2, st>>>(
-      ta, tw, tout, thm, hm_period, use_tma_store, bias, row_mask, static_cast<OutT*>(out), static_cast<int>(M), Nout,
+      ta, *nchw_a, tw, tout, thm, hm_period, use_tma_store, bias, row_mask, static_cast<OutT*>(out), static_cast<int>(M), Nout,
       K, NC, n_chunks, groups, ldo, relu);
   return check_launch("mvg_linear_bf16");
 }
@@ -455,6 +484,69 @@ extern "C" int mvg_linear_bf16(const void* A, const void* W, const float* bias, 
   return MVG_EUNSUPPORTED;
 }
 
+
+// 3-D bf16 map over one NCHW pyramid level (rows, 256, HW): dims {HW, 256, rows}, box {64 texels, 64 channels, 1}.
+static int make_nchw_level_tmap(CUtensorMap* map, const void* ptr, int64_t hw, int64_t rows) {
+  mvg::EncodeTiledFn enc = mvg::get_encode_fn();
+  if (!enc) {
+    mvg::set_error("cuTensorMapEncodeTiled entry point not available");
+    return MVG_ELAUNCH;
+  }
+  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(hw), 256, static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(hw) * 2, static_cast<cuuint64_t>(hw) * 512};
+  const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(mvg::kBlockK), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mvg::set_error("cuTensorMapEncodeTiled(nchw level) failed (%d) hw=%lld rows=%lld", static_cast<int>(r),
+                   static_cast<long long>(hw), static_cast<long long>(rows));
+    return MVG_ELAUNCH;
+  }
+  return MVG_OK;
+}
+
+extern "C" int mvg_value_proj_gemm_nchw_supported(int num_levels, const int* level_hw) {
+  if (level_hw == nullptr || num_levels < 1 || num_levels > MVG_MAX_LEVELS) return 0;
+  for (int l = 0; l < num_levels; ++l)
+    if (level_hw[l] <= 0 || level_hw[l] % mvg::kBlockM != 0) return 0;
+  return 1;
+}
+
+extern "C" int mvg_value_proj_gemm_nchw(const void* const* src_levels, int num_levels, const int* level_hw,
+                                        int rows, const void* W, const float* bias, int layers, void* value_hm,
+                                        void* gmap, void* stream) {
+  using namespace mvg;
+  MVG_REQUIRE(src_levels && level_hw && W && value_hm && gmap, "mvg_value_proj_gemm_nchw: null pointer");
+  MVG_REQUIRE(mvg_value_proj_gemm_nchw_supported(num_levels, level_hw),
+              "mvg_value_proj_gemm_nchw: every level needs H*W %% %d == 0 (use mvg_pyramid_to_channels_last + "
+              "mvg_value_proj_gemm otherwise)", kBlockM);
+  MVG_REQUIRE(rows > 0 && layers > 0 && layers * 448 <= 148 * 256, "mvg_value_proj_gemm_nchw: bad shape");
+  NchwA na{};
+  na.num_levels = num_levels;
+  int64_t S = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    MVG_REQUIRE(src_levels[l] != nullptr && (reinterpret_cast<uintptr_t>(src_levels[l]) & 15) == 0,
+                "mvg_value_proj_gemm_nchw: level %d pointer null / not 16-byte aligned", l);
+    na.tile_start[l] = static_cast<int>(S / kBlockM);
+    int rc = make_nchw_level_tmap(&na.map[l], src_levels[l], level_hw[l], rows);
+    if (rc) return rc;
+    S += level_hw[l];
+  }
+  na.tile_start[num_levels] = static_cast<int>(S / kBlockM);
+  na.tiles_per_row = static_cast<int>(S / kBlockM);
+  const int64_t M = static_cast<int64_t>(rows) * S;
+  MVG_REQUIRE(M < (1ll << 31), "mvg_value_proj_gemm_nchw: too many rows");
+  const void* ptrs[] = {W, value_hm, gmap};
+  for (const void* q : ptrs)
+    MVG_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0, "mvg_value_proj_gemm_nchw: operands must be 16-byte aligned");
+  MVG_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+              "mvg_value_proj_gemm_nchw: bias must be 16-byte aligned");
+  return launch_linear<__nv_bfloat16>(nullptr, W, bias, nullptr, gmap, M, layers * 448, 256,
+                                      static_cast<int64_t>(layers) * 192, 0, static_cast<cudaStream_t>(stream),
+                                      value_hm, &na);
+}
 
 extern "C" int mvg_value_proj_gemm(const void* feat, const void* W, const float* bias, int64_t M, int layers,
                                    void* value_hm, void* gmap, void* stream) {

@@ -24,6 +24,8 @@ triangulation_method='linalg') is not reproduced.
 """
 from __future__ import annotations
 
+import os
+
 import copy
 from typing import Dict, List, Optional, Sequence
 
@@ -95,8 +97,12 @@ class DecoderContext:
             dev = src_views[0].device
             self.levels = [(int(s.shape[2]), int(s.shape[3])) for s in src_views]
             rows = src_views[0].shape[0]
-            with prof.stage("pyramid_to_cl"):
-                feat_cl = ops.pyramid_to_channels_last(src_views)            # (V*B,S,256) bf16
+            # bf16 NCHW levels of 128-texel multiples are read in place by the GEMM (MN-major TMA operand);
+            # anything else (fp32 maps, odd level sizes) goes through the channels-last hand-off kernel
+            feat_cl = None
+            if not (ops.value_proj_nchw_supported(src_views) and os.environ.get("MVG_NCHW_GEMM", "1") != "0"):
+                with prof.stage("pyramid_to_cl"):
+                    feat_cl = ops.pyramid_to_channels_last(src_views)        # (V*B,S,256) bf16
         self.batch = batch_size
         self.views = rows // batch_size
         self.img_size = [float(img_size[0]), float(img_size[1])]
@@ -119,7 +125,10 @@ class DecoderContext:
             w_all, b_all = cached[1], cached[2]
         with prof.stage("vg_gemm"):
             # value (head-major) + offset/logit map G for all distinct layers, one GEMM
-            self.value_hm, self.gmap = ops.value_proj(feat_cl, w_all, b_all, len(distinct))
+            if feat_cl is None:
+                self.value_hm, self.gmap = ops.value_proj_nchw(list(src_views), w_all, b_all, len(distinct))
+            else:
+                self.value_hm, self.gmap = ops.value_proj(feat_cl, w_all, b_all, len(distinct))
         self.ld_g = self.gmap.shape[-1]
         self.value_head_stride = self.value_hm.stride(0)
         self._slot = {id(l): i for i, l in enumerate(distinct)}

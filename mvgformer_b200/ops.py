@@ -95,6 +95,41 @@ def value_proj(feat_cl: torch.Tensor, w_all: torch.Tensor, b_all: Optional[torch
     return value_hm, gmap
 
 
+def value_proj_nchw_supported(src_views) -> bool:
+    """True when `value_proj_nchw` can read these pyramid levels in place: bf16, contiguous NCHW, 256
+    channels, H_l * W_l a multiple of 128, tcgen05 backend."""
+    from .linear import get_backend
+    if isinstance(src_views, PackedPyramid) or get_backend() != "tcgen05":
+        return False
+    for s in src_views:
+        if s.dtype != torch.bfloat16 or s.dim() != 4 or s.shape[1] != 256 or not s.is_contiguous() \
+                or (s.shape[2] * s.shape[3]) % 128 != 0 or s.shape[0] != src_views[0].shape[0] \
+                or s.data_ptr() % 16 != 0:
+            return False
+    return 0 < len(src_views) <= _lib.MVG_MAX_LEVELS
+
+
+def value_proj_nchw(src_views: Sequence[torch.Tensor], w_all: torch.Tensor, b_all: Optional[torch.Tensor],
+                    layers: int):
+    """`value_proj` reading the NCHW pyramid levels in place (no channels-last copy): the GEMM's TMA
+    producer loads 128-texel tiles of the (rows, 256, H_l, W_l) maps as an MN-major tcgen05 operand.
+    Same outputs as `value_proj(pyramid_to_channels_last(src_views), ...)`."""
+    lib = _lib.load()
+    _lib.require_cuda(*src_views)
+    rows = src_views[0].shape[0]
+    hw = [s.shape[2] * s.shape[3] for s in src_views]
+    M = rows * sum(hw)
+    dev = src_views[0].device
+    value_hm = torch.empty((layers * 8, M, 32), dtype=torch.float16, device=dev)
+    gmap = torch.empty((M, layers * 192), dtype=torch.float16, device=dev)
+    ptrs = (C.c_void_p * len(src_views))(*[s.data_ptr() for s in src_views])
+    hws = (C.c_int * len(src_views))(*hw)
+    check(lib.mvg_value_proj_gemm_nchw(ptrs, len(src_views), hws, rows, w_all.data_ptr(), _lib.ptr(b_all), layers,
+                                       value_hm.data_ptr(), gmap.data_ptr(), stream_ptr(dev)),
+          "mvg_value_proj_gemm_nchw")
+    return value_hm, gmap
+
+
 def make_sample_params(batch: int, views: int, points: int, levels: Sequence[Tuple[int, int]],
                        ld_g: int, img_size: Sequence[float], value_head_stride: int) -> MvgSampleParams:
     prm = MvgSampleParams()

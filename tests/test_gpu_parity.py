@@ -185,6 +185,33 @@ def test_pyramid_to_channels_last():
     assert torch.equal(out2, ref)
 
 
+@pytest.mark.parametrize("rows,levels,layers", [(2, [(16, 24), (8, 16)], 1), (3, [(32, 60), (16, 32), (8, 16)], 2),
+                                                (5, [(128, 240), (64, 120), (32, 60)], 4)])
+def test_value_proj_nchw_equals_channels_last_path(rows, levels, layers):
+    """mvg_value_proj_gemm_nchw (the NCHW levels loaded in place as an MN-major tcgen05 operand) writes the
+    same value / G maps, bit for bit, as mvg_pyramid_to_channels_last + mvg_value_proj_gemm - up to the full
+    Panoptic pyramid with all four layers' weights; and both agree with an fp32 matmul."""
+    g = torch.Generator(device="cpu").manual_seed(rows)
+    src = [torch.randn(rows, 256, h, w, generator=g).to(DEV).to(torch.bfloat16) for h, w in levels]
+    w_all = (torch.randn(layers * 448, 256, generator=g) * 0.05).to(DEV).to(torch.bfloat16)
+    b_all = torch.randn(layers * 448, generator=g).to(DEV)
+    assert ops.value_proj_nchw_supported(src)
+    feat_cl = ops.pyramid_to_channels_last(src)
+    v0, g0 = ops.value_proj(feat_cl, w_all, b_all, layers)
+    v1, g1 = ops.value_proj_nchw(src, w_all, b_all, layers)
+    assert torch.equal(v0, v1) and torch.equal(g0, g1)
+    M = feat_cl.shape[0] * feat_cl.shape[1]
+    pick = torch.randint(0, M, (4096,), generator=g).to(DEV)
+    y = feat_cl.view(M, 256)[pick].float() @ w_all.float().t() + b_all          # (4096, layers*448)
+    y = y.view(-1, layers, 448)
+    val = v1.permute(1, 0, 2)[pick].reshape(-1, layers, 256).float()             # heads of a layer are adjacent
+    assert (val - y[:, :, :256]).abs().max() < 2e-2
+    assert (g1[pick].view(-1, layers, 192).float() - y[:, :, 256:]).abs().max() < 2e-2
+    # levels that are not 128-texel multiples / fp32 maps are refused here and take the hand-off kernel
+    assert not ops.value_proj_nchw_supported([torch.zeros(1, 256, 19, 25, device=DEV, dtype=torch.bfloat16)])
+    assert not ops.value_proj_nchw_supported([s.float() for s in src])
+
+
 def test_elementwise_kernels():
     rng = np.random.default_rng(1)
     B, V, N, C = 2, 3, 45, 256
