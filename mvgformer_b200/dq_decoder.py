@@ -245,7 +245,10 @@ class DQDecoderLayer(nn.Module):
 
     # ------------------------------------------------------------------ the layer
     def _forward_ctx(self, tgt, query_pos, reference_points, ctx: DecoderContext, *,
-                     threshold, indices=None, return_debug=False, shard=None):
+                     threshold, indices=None, return_debug=False, shard=None, outs=None):
+        """`outs` = (tgt_out (B,N,256), ref_out (B,N,3), refined_out (B,V,N,2), projs_out (B,V,N,2)): the
+        kernels write this layer's results straight into them (DQDecoder passes the slices of its stacked
+        return tensors, so no torch.stack copy follows)."""
         if _wants_autograd(self, tgt, query_pos, reference_points):
             # the fused path detaches its inputs and applies no dropout: refuse to pretend
             raise RuntimeError(
@@ -287,13 +290,16 @@ class DQDecoderLayer(nn.Module):
                 # feature_update_mlp + norm2 + FFN + norm3 in one kernel (csrc/ffn_chain.cu)
                 tgt_update = ops.ffn_chain(aver, tgt, lw["w_fu"], lw["b_fu"], lw["g2"], lw["e2"],
                                            self.norm2.eps, lw["w1"], lw["b1"], lw["w2"], lw["b2"],
-                                           lw["g3"], lw["e3"], self.norm3.eps)
+                                           lw["g3"], lw["e3"], self.norm3.eps,
+                                           out=None if outs is None else outs[0])
             else:
                 t2 = linear(aver, lw["w_fu"], lw["b_fu"])
                 tu, tu_bf = ops.add_layernorm(tgt, t2, lw["g2"], lw["e2"], self.norm2.eps)
                 hdn = linear(tu_bf, lw["w1"], lw["b1"], relu=True)
                 ff = linear(hdn, lw["w2"], lw["b2"])
                 tgt_update, _ = ops.add_layernorm(tu, ff, lw["g3"], lw["e3"], self.norm3.eps, want_bf16=False)
+                if outs is not None:
+                    tgt_update = outs[0].copy_(tgt_update)
         # 5. class head + query filter (integer path)
         with prof.stage("class_head"):
             prob = ops.class_head(tgt_update, lw["wc"], lw["bc"], Q, J)           # (B,Q,2)
@@ -337,7 +343,8 @@ class DQDecoderLayer(nn.Module):
         # 7. offsets -> undistort -> DLT -> scatter
         with prof.stage("offsets_dlt"):
             new_ref, refined_abs, projs_abs = ops.offsets_dlt(mlp_out, ref2d, selected, ctx.cams,
-                                                              Q, J, ctx.img_size)
+                                                              Q, J, ctx.img_size,
+                                                              outs=None if outs is None else outs[1:4])
         out = (tgt_update, new_ref, refined_abs, projs_abs, prob)
         if return_debug:
             return out, dict(sampled=sampled, ref2d=ref2d, bounding=bounding, attn=attn,
@@ -414,6 +421,15 @@ class DQDecoder(nn.Module):
         inter, inter_ref, inter_2d, inter_proj, classes = [], [], [], [], []
         ref_points_2d = None
         counts = []
+        stacked = None
+        if self.return_intermediate and not train:
+            # the stacked return tensors are allocated once and every layer writes its slice in place
+            # (torch.stack of the per-layer outputs was a 63 MB copy per call)
+            Lr, (Bq, Nq, _), Vq = len(self.layers), tgt.shape, ctx.views
+            stacked = (torch.empty((Lr, Bq, Nq, 256), dtype=torch.float32, device=tgt.device),
+                       torch.empty((Lr, Bq, Nq, 3), dtype=torch.float32, device=tgt.device),
+                       torch.empty((Lr, Bq, Vq, Nq, 2), dtype=torch.float32, device=tgt.device),
+                       torch.empty((Lr, Bq, Vq, Nq, 2), dtype=torch.float32, device=tgt.device))
         for lid, layer in enumerate(self.layers):
             lshard = shard
             if shard is not None:
@@ -426,7 +442,8 @@ class DQDecoder(nn.Module):
             else:
                 output, reference_points, ref_points_2d, projs_2d_absolute, outputs_class = \
                     layer._forward_ctx(output, query_pos, reference_points, ctx, threshold=threshold,
-                                       indices=indices, shard=lshard)
+                                       indices=indices, shard=lshard,
+                                       outs=None if stacked is None else tuple(t[lid] for t in stacked))
             if shard is not None:
                 counts.append(layer._shard_count)
             if self.return_intermediate:
@@ -436,6 +453,8 @@ class DQDecoder(nn.Module):
                 inter_proj.append(projs_2d_absolute)
                 classes.append(outputs_class)
         self.last_shard_counts = torch.cat(counts) if counts else None     # (L,) int32, device
+        if stacked is not None:
+            return stacked[0], stacked[1], stacked[2], stacked[3], classes
         if self.return_intermediate:
             return torch.stack(inter), torch.stack(inter_ref), torch.stack(inter_2d), \
                 torch.stack(inter_proj), classes

@@ -266,14 +266,21 @@ def select_pad(prob: torch.Tensor, threshold: float, method: str = "threshold",
 
 
 def offsets_dlt(mlp_out: torch.Tensor, ref2d: torch.Tensor, selected: torch.Tensor,
-                cams: torch.Tensor, queries: int, joints: int, img_size: Sequence[float]):
-    """-> new_ref (B,N,3), refined_abs (B,V,N,2), projs_abs (B,V,N,2) fp32."""
+                cams: torch.Tensor, queries: int, joints: int, img_size: Sequence[float], outs=None):
+    """-> new_ref (B,N,3), refined_abs (B,V,N,2), projs_abs (B,V,N,2) fp32 (written into `outs` when
+    given: three contiguous fp32 tensors of those shapes)."""
     lib = _lib.load()
     B, V, N, _ = ref2d.shape
     dev = ref2d.device
-    new_ref = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
-    refined = torch.empty((B, V, N, 2), dtype=torch.float32, device=dev)
-    projs = torch.empty((B, V, N, 2), dtype=torch.float32, device=dev)
+    if outs is None:
+        new_ref = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+        refined = torch.empty((B, V, N, 2), dtype=torch.float32, device=dev)
+        projs = torch.empty((B, V, N, 2), dtype=torch.float32, device=dev)
+    else:
+        new_ref, refined, projs = outs
+        for t, shp in ((new_ref, (B, N, 3)), (refined, (B, V, N, 2)), (projs, (B, V, N, 2))):
+            if tuple(t.shape) != shp or t.dtype != torch.float32 or not t.is_contiguous():
+                raise _lib.MvgError("offsets_dlt: `outs` must be contiguous float32 tensors (B,N,3), (B,V,N,2) x 2")
     check(lib.mvg_offsets_dlt(mlp_out.data_ptr(), int(mlp_out.stride(-2)), ref2d.data_ptr(), selected.data_ptr(),
                               cams.data_ptr(), B, V, queries, joints, float(img_size[0]),
                               float(img_size[1]), new_ref.data_ptr(), refined.data_ptr(),
@@ -348,13 +355,17 @@ def add_cast_bf16(a: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
 
 
 def ffn_chain(aver: torch.Tensor, tgt: torch.Tensor, w_fu, b_fu, g2, e2, eps2, w1, b1, w2, b2, g3, e3,
-              eps3) -> torch.Tensor:
+              eps3, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """LayerNorm(tu + FFN(tu)), tu = LayerNorm(tgt + aver @ w_fu^T + b_fu) in one tcgen05 kernel.
-    aver (..., 256) bf16, tgt (..., 256) fp32 -> (..., 256) fp32."""
+    aver (..., 256) bf16, tgt (..., 256) fp32 -> (..., 256) fp32 (into `out` when given: a contiguous
+    fp32 tensor of tgt's shape, e.g. this layer's slice of the stacked decoder output)."""
     lib = _lib.load()
     _lib.require_cuda(aver, tgt)
     M = aver.numel() // aver.shape[-1]
-    out = torch.empty(tgt.shape, dtype=torch.float32, device=tgt.device)
+    if out is None:
+        out = torch.empty(tgt.shape, dtype=torch.float32, device=tgt.device)
+    elif out.shape != tgt.shape or out.dtype != torch.float32 or not out.is_contiguous():
+        raise _lib.MvgError("ffn_chain: `out` must be a contiguous float32 tensor of tgt's shape")
     check(lib.mvg_ffn_chain(aver.data_ptr(), tgt.data_ptr(), w_fu.data_ptr(), b_fu.data_ptr(), g2.data_ptr(),
                             e2.data_ptr(), float(eps2), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
                             b2.data_ptr(), g3.data_ptr(), e3.data_ptr(), float(eps3), M, int(w1.shape[0]),
