@@ -21,29 +21,13 @@ masked_view_mean_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __re
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  // views in batches of 8: all flags, then all rows of the batch are in flight before the first add (a
-  // flag -> branch -> row chain per view made this kernel five dependent L2 round trips long)
-  for (int v0 = 0; v0 < V; v0 += 8) {
-    bool ok[8];
-    uint4 xv[8];
+  for (int v = 0; v < V; ++v) {
+    const int64_t row = (static_cast<int64_t>(b) * V + v) * N + n;
+    if (bounding[row]) {
+      float t[8];
+      unpack8(ldg_nc_v4(x + row * C + cv * 8), t);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int v = v0 + j;
-      ok[j] = v < V && bounding[(static_cast<int64_t>(b) * V + (v < V ? v : 0)) * N + n] != 0;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int64_t row = (static_cast<int64_t>(b) * V + v0 + j) * N + n;
-      xv[j] = ok[j] ? ldg_nc_v4(x + row * C + cv * 8) : make_uint4(0u, 0u, 0u, 0u);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {          // same order of additions as before: v ascending, skipped views add nothing
-      if (ok[j]) {
-        float t[8];
-        unpack8(xv[j], t);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += t[i];
-      }
+      for (int i = 0; i < 8; ++i) acc[i] += t[i];
     }
   }
   const float inv = 1.f / static_cast<float>(V);
