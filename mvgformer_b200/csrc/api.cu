@@ -1,10 +1,20 @@
 // Error plumbing + version for libmvg_b200.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mvg {
 
 static thread_local char t_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("MVG_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -38,6 +38,33 @@ inline int check_launch(const char* what) {
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------
+// The kernels of a decoder step form one dependent chain of ~60 launches, most of them 3-40 us long.
+// Launched with the programmatic-stream-serialization attribute, kernel i+1's CTAs are scheduled as the
+// CTAs of kernel i drain (every kernel calls pdl_enter() before its first global access: wait for the
+// whole previous grid + its memory flush, then allow the NEXT kernel's early launch), so launch latency
+// and CTA start-up overlap the previous kernel's tail instead of following it.  MVG_PDL=0 disables the
+// attribute (plain stream order; pdl_enter() is then a no-op pair of instructions).
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);     // errors surface in check_launch()
+}
+
 // ---- packed camera record: MVG_CAM_FLOATS = 64 fp32 per (frame, view) --------------------
 // Filled by mvgformer_b200/cameras.py::pack_cameras (host-side mirror of
 // unfold_camera_param_batch / get_affine_transform / get_proj_matricies_batch).

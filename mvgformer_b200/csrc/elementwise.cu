@@ -10,6 +10,7 @@ namespace mvg {
 __global__ void __launch_bounds__(256)
 masked_view_mean_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ bounding,
                         int B, int V, int64_t N, int C, __nv_bfloat16* __restrict__ out) {
+  pdl_enter();
   const int vec_per_row = C / 8;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = static_cast<int64_t>(B) * N * vec_per_row;
@@ -154,6 +155,7 @@ class_head_kernel(const float* __restrict__ x, const float* __restrict__ w,
 __global__ void __launch_bounds__(256)
 add_cast_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n8,
                      __nv_bfloat16* __restrict__ out) {
+  pdl_enter();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const float4 a0 = __ldg(reinterpret_cast<const float4*>(a) + 2 * i);
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(512)
 class_head_kernel_v2(const float* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ bias, int J, float* __restrict__ prob) {
   __shared__ float part[16][2];
+  pdl_enter();
   const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
   const int64_t bq = blockIdx.x;
   if (j < J) {
@@ -213,8 +216,8 @@ extern "C" int mvg_add_cast_bf16(const float* a, const float* b, void* out_bf16,
   using namespace mvg;
   MVG_REQUIRE(a && out_bf16 && n > 0 && n % 8 == 0, "mvg_add_cast_bf16: bad argument (n must be a multiple of 8)");
   const int64_t n8 = n / 8;
-  add_cast_bf16_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      a, b, n8, static_cast<__nv_bfloat16*>(out_bf16));
+  launch_k(add_cast_bf16_kernel, dim3(static_cast<unsigned>((n8 + 255) / 256)), dim3(256), 0,
+           static_cast<cudaStream_t>(stream), a, b, n8, static_cast<__nv_bfloat16*>(out_bf16));
   return check_launch("mvg_add_cast_bf16");
 }
 
@@ -225,8 +228,8 @@ extern "C" int mvg_class_head(const float* x, const float* w, const float* bias,
               "mvg_class_head: bad argument");
   const int64_t bq = static_cast<int64_t>(batch) * queries;
   if (joints <= 16)
-    class_head_kernel_v2<<<static_cast<unsigned>(bq), joints * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, w, bias, joints, prob);
+    launch_k(class_head_kernel_v2, dim3(static_cast<unsigned>(bq)), dim3(joints * 32), 0,
+             static_cast<cudaStream_t>(stream), x, w, bias, joints, prob);
   else
     class_head_kernel<<<static_cast<unsigned>((bq + 7) / 8), 256, 0,
                         static_cast<cudaStream_t>(stream)>>>(x, w, bias, bq, joints, prob);
@@ -240,10 +243,9 @@ extern "C" int mvg_masked_view_mean(const void* x_bf16, const uint8_t* bounding,
   MVG_REQUIRE(x_bf16 && bounding && out_bf16, "mvg_masked_view_mean: null pointer");
   MVG_REQUIRE(channels % 8 == 0 && batch > 0 && views > 0 && points > 0, "mvg_masked_view_mean: bad shape");
   const int64_t total = static_cast<int64_t>(batch) * points * (channels / 8);
-  masked_view_mean_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
-                            static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x_bf16), bounding, batch, views, points, channels,
-      static_cast<__nv_bfloat16*>(out_bf16));
+  launch_k(masked_view_mean_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0,
+           static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x_bf16), bounding, batch, views,
+           static_cast<int64_t>(points), channels, static_cast<__nv_bfloat16*>(out_bf16));
   return check_launch("mvg_masked_view_mean");
 }
 

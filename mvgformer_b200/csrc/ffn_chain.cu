@@ -288,6 +288,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc1 = tmem_base, acc2 = tmem_base + 256;
+  pdl_enter();               // barriers / TMEM are set up; everything below touches global memory
   if (threadIdx.x == 0) FFN_STAMP(40);
 
   if (warp == 0) {
@@ -539,7 +540,8 @@ extern "C" int mvg_ffn_chain(const void* aver_bf16, const float* tgt, const void
   FfnChainParams p{tgt, b_fu, g2, e2, b1, b2, g3, e3, out, static_cast<int>(M), d_ffn / kFcHC, eps2, eps3};
   const int m_tiles = static_cast<int>((M + kBlockM - 1) / kBlockM);
   const int grid = m_tiles < kNumSMs ? m_tiles : kNumSMs;
-  ffn_chain_kernel<<<grid, kFcThreads, kFcSmemBytes, static_cast<cudaStream_t>(stream)>>>(tx, tfu, tw1, tw2, p);
+  launch_k(ffn_chain_kernel, dim3(grid), dim3(kFcThreads), kFcSmemBytes, static_cast<cudaStream_t>(stream), tx, tfu, tw1,
+           tw2, p);
   return check_launch("mvg_ffn_chain");
 }
 

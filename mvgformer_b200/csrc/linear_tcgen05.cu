@@ -102,6 +102,7 @@ linear_tcgen05_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_enter();               // barriers / TMEM are set up; everything below touches global memory
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -450,9 +451,9 @@ static int launch_linear(const void* A, const void* W, const float* bias, const 
     }
     attr_set = true;
   }
-  kern<<<n_chunks * groups, kGemmThreadsV2, kSmemBytesV2, st>>>(
-      ta, *nchw_a, tw, tout, thm, hm_period, use_tma_store, bias, row_mask, static_cast<OutT*>(out), static_cast<int>(M), Nout,
-      K, NC, n_chunks, groups, ldo, relu);
+  launch_k(kern, dim3(n_chunks * groups), dim3(kGemmThreadsV2), kSmemBytesV2, st, ta, *nchw_a, tw, tout, thm, hm_period,
+           use_tma_store, bias, row_mask, static_cast<OutT*>(out), static_cast<int>(M), Nout, K, NC, n_chunks, groups,
+           ldo, relu);
   return check_launch("mvg_linear_bf16");
 }
 

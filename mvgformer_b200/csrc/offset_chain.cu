@@ -97,6 +97,7 @@ offset_chain_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_enter();               // the row count below is the previous kernel's (mvg_select_pad) output
   const int64_t n_active = static_cast<int64_t>(__ldg(p.info)) * p.views * p.joints;
   const int m_tiles = static_cast<int>((n_active + kBlockM - 1) / kBlockM);
 
@@ -336,6 +337,6 @@ extern "C" int mvg_offset_chain(const void* attn_bf16, const int32_t* info, cons
                       out_ld, views, joints, queries * joints};
   const int64_t max_tiles = (rows + kBlockM - 1) / kBlockM;
   const int grid = static_cast<int>(max_tiles < kNumSMs ? max_tiles : kNumSMs);
-  offset_chain_kernel<<<grid, kOcThreads, kOcSmemBytes, static_cast<cudaStream_t>(stream)>>>(t1, t2, p);
+  launch_k(offset_chain_kernel, dim3(grid), dim3(kOcThreads), kOcSmemBytes, static_cast<cudaStream_t>(stream), t1, t2, p);
   return check_launch("mvg_offset_chain");
 }

@@ -141,6 +141,7 @@ offsets_dlt_kernel(const float* __restrict__ mlp_out, int mlp_ld, const float* _
                    int B, int V, int Q, int J, float img_w, float img_h,
                    float* __restrict__ new_ref, float* __restrict__ refined_abs,
                    float* __restrict__ projs_abs) {
+  pdl_enter();
   const int64_t N = static_cast<int64_t>(Q) * J;
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t idx = gid / kDltLanes;                   // problem
@@ -268,10 +269,9 @@ extern "C" int mvg_offsets_dlt(const float* mlp_out, int mlp_ld, const float* re
   MVG_REQUIRE(mlp_ld >= 3, "mvg_offsets_dlt: mlp_ld %d < 3", mlp_ld);
   const int64_t total = static_cast<int64_t>(batch) * queries * joints * kDltLanes;
   const int threads = 128;
-  offsets_dlt_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0,
-                       static_cast<cudaStream_t>(stream)>>>(
-      mlp_out, mlp_ld, ref2d, selected, reinterpret_cast<const MvgCamera*>(cams), batch, views, queries,
-      joints, img_w, img_h, new_ref, refined_abs, projs_abs);
+  launch_k(offsets_dlt_kernel, dim3(static_cast<unsigned>((total + threads - 1) / threads)), dim3(threads), 0,
+           static_cast<cudaStream_t>(stream), mlp_out, mlp_ld, ref2d, selected, reinterpret_cast<const MvgCamera*>(cams),
+           batch, views, queries, joints, img_w, img_h, new_ref, refined_abs, projs_abs);
   return check_launch("mvg_offsets_dlt");
 }
 

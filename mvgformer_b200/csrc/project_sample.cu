@@ -211,6 +211,7 @@ project_bin_kernel(const float* __restrict__ ref3d, const MvgCamera* __restrict_
                    const MvgSampleParams prm, float* __restrict__ ref2d_out,
                    uint8_t* __restrict__ bounding_out, __nv_bfloat16* __restrict__ sampled,
                    const GatherWs ws) {
+  pdl_enter();
   const int N = prm.points, V = prm.views;
   const int bv = blockIdx.y;
   const int n = blockIdx.x * kPcThreads + threadIdx.x;
@@ -291,6 +292,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
 __global__ void __launch_bounds__(kScanThreads)
 bin_scan_kernel(const GatherWs ws, int cells_per_bv) {
   __shared__ int warp_sums[32];
+  pdl_enter();
   int carry_items = 0, carry_chunks = 0;
   for (int base = 0; base < ws.keys; base += kScanThreads) {
     const int k = base + threadIdx.x;
@@ -329,6 +331,7 @@ bin_scan_kernel(const GatherWs ws, int cells_per_bv) {
 }
 
 __global__ void __launch_bounds__(256) bin_scatter_kernel(const GatherWs ws) {
+  pdl_enter();
   const int64_t item = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (item >= ws.items) return;
   const int key = ws.item_key[item];
@@ -373,6 +376,7 @@ sample_params_kernel(const __half* __restrict__ gmap, const float* __restrict__ 
   ParamScratch<LV>* scratch = reinterpret_cast<ParamScratch<LV>*>(smem_dyn);        // [kPWarps]
   __shared__ int s_bb[kHeads][LV][4];     // x0 min, y0 min, x0 max, y0 max
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_enter();
   using PS = ParamScratch<LV>;
   PS& sc = scratch[warp];
   const int N = prm.points, V = prm.views, B = prm.batch;
@@ -761,6 +765,7 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_enter();               // barriers are set up; everything below reads the previous kernels' outputs
   const int V = prm.views, B = prm.batch;
 
   if (warp == kGWarps) {
@@ -945,6 +950,7 @@ __global__ void __launch_bounds__(256)
 gather_direct_kernel(const __half* __restrict__ value_hm, const MvgSampleParams prm,
                      __nv_bfloat16* __restrict__ sampled, const GatherWs ws) {
   const int lane = threadIdx.x & 31;
+  pdl_enter();
   const int n_direct = ws.ctrs[3];
   const int q = lane >> 3, dx = (lane >> 2) & 1;
   const int chn = lane_channel(lane);
@@ -1002,15 +1008,15 @@ static int launch_gather(const __half* vhm, const __half* gmp, const float* qpro
   const int64_t chunks_bound = ws.items / kChunk + ws.keys + 1;
   const int64_t parts_bound = chunks_bound * kParts;
   const int pgrid = static_cast<int>(parts_bound < MVG_P_MINBLK * kNumSMs ? parts_bound : MVG_P_MINBLK * kNumSMs);
-  sample_params_kernel<LV><<<pgrid, kPWarps * 32, psmem, st>>>(gmp, qproj, prm, ref2d, refl_in, ws);
+  launch_k(sample_params_kernel<LV>, dim3(pgrid), dim3(kPWarps * 32), psmem, st, gmp, qproj, prm, ref2d, refl_in, ws);
   int rc = check_launch("mvg_project_sample_fused(sample_params)");
   if (rc != MVG_OK) return rc;
   const int64_t units_bound = chunks_bound * kHeads;
   const int ggrid = static_cast<int>(units_bound < kNumSMs ? units_bound : kNumSMs);
-  gather_tiles_kernel<LV><<<ggrid, (kGWarps + 1) * 32, smem, st>>>(vhm, prm, sp, ws);
+  launch_k(gather_tiles_kernel<LV>, dim3(ggrid), dim3((kGWarps + 1) * 32), smem, st, vhm, prm, sp, ws);
   rc = check_launch("mvg_project_sample_fused(gather_tiles)");
   if (rc != MVG_OK) return rc;
-  gather_direct_kernel<LV><<<kNumSMs, 256, 0, st>>>(vhm, prm, sp, ws);
+  launch_k(gather_direct_kernel<LV>, dim3(kNumSMs), dim3(256), 0, st, vhm, prm, sp, ws);
   return check_launch("mvg_project_sample_fused(gather_direct)");
 }
 
@@ -1067,18 +1073,18 @@ static int run_project_bin(const float* ref3d, const float* cams, const MvgSampl
   const dim3 pc_grid((prm->points + kPcThreads - 1) / kPcThreads, static_cast<unsigned>(BV));
   int rc;
   if (refl_in == nullptr) {
-    project_bin_kernel<<<pc_grid, kPcThreads, 0, st>>>(ref3d, reinterpret_cast<const MvgCamera*>(cams), *prm, ref2d,
-                                                       bounding, static_cast<__nv_bfloat16*>(sampled), ws);
+    launch_k(project_bin_kernel, pc_grid, dim3(kPcThreads), 0, st, ref3d, reinterpret_cast<const MvgCamera*>(cams), *prm,
+             ref2d, bounding, static_cast<__nv_bfloat16*>(sampled), ws);
     rc = check_launch("mvg_project_bin(project_bin)");
   } else {
     bin_refl_kernel<<<pc_grid, kPcThreads, 0, st>>>(refl_in, *prm, ws);
     rc = check_launch("mvg_project_bin(bin_refl)");
   }
   if (rc != MVG_OK) return rc;
-  bin_scan_kernel<<<1, kScanThreads, 0, st>>>(ws, ws.kx * ws.ky);
+  launch_k(bin_scan_kernel, dim3(1), dim3(kScanThreads), 0, st, ws, ws.kx * ws.ky);
   rc = check_launch("mvg_project_bin(bin_scan)");
   if (rc != MVG_OK) return rc;
-  bin_scatter_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(ws);
+  launch_k(bin_scatter_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, ws);
   return check_launch("mvg_project_bin(bin_scatter)");
 }
 

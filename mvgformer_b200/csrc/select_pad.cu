@@ -24,6 +24,7 @@ select_pad_kernel(const float* __restrict__ prob, int B, int Q, float thr, int m
   int* s_count = s_dyn;
   int* s_prefix = s_dyn + B;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_enter();
 
   // pass 1: mask + per-frame counts
   for (int b = 0; b < B; ++b) {
@@ -112,8 +113,8 @@ extern "C" int mvg_select_pad(const float* prob, int batch, int queries, float t
   const bool ids = batch_ids || query_ids || batch_ids_rev || query_ids_rev;
   MVG_REQUIRE(!ids || (batch_ids && query_ids && batch_ids_rev && query_ids_rev),
               "mvg_select_pad: id arrays must be all set or all NULL");
-  select_pad_kernel<<<1, 1024, 2 * batch * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
-      prob, batch, queries, threshold, method, min_one, selected, counts, info, batch_ids, query_ids,
-      batch_ids_rev, query_ids_rev);
+  launch_k(select_pad_kernel, dim3(1), dim3(1024), 2 * batch * sizeof(int), static_cast<cudaStream_t>(stream), prob, batch,
+           queries, threshold, method, min_one, selected, counts, info, batch_ids, query_ids, batch_ids_rev,
+           query_ids_rev);
   return check_launch("mvg_select_pad");
 }

@@ -12,7 +12,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s ${LIST_
   > gpurun_out/launches_$tag.log 2>&1
 # one decoder layer + the per-call kernels (camera packing, pyramid hand-off, value GEMM): ~20 launches, ~40 replays each.
 # Keep the report small: gpurun merges at most 64 MiB back.
-timeout 600 ncu --set full --clock-control none -k regex:"^(pack_cameras|pyramid_to_cl|linear_tcgen05|add_cast|project_bin|bin_scan|bin_scatter|sample_params|gather_tiles|gather_direct|masked_view_mean|ffn_chain|class_head|select_pad|offset_chain|offsets_dlt)" -s ${NCU_SKIP:-189} -c ${NCU_COUNT:-18} -o gpurun_out/step_$tag \
+timeout 600 ncu --set full --clock-control none -k regex:"^(pack_cameras|pyramid_to_cl|linear_tcgen05|add_cast|project_bin|bin_scan|bin_scatter|sample_params|gather_tiles|gather_direct|masked_view_mean|ffn_chain|class_head|select_pad|offset_chain|offsets_dlt)" -s ${NCU_SKIP:-186} -c ${NCU_COUNT:-18} -o gpurun_out/step_$tag \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-graph --no-parity > gpurun_out/step_$tag.log 2>&1
 tail -2 gpurun_out/step_$tag.log | cut -c1-200
 ls -la gpurun_out/
