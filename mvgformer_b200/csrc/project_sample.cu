@@ -47,6 +47,10 @@
 //                        keeps the operator correct for arbitrary offsets).
 // Results do not depend on the (non-deterministic) order of items inside a key: every item's
 // arithmetic is a fixed sequence over its own records.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
 #include "tcgen05.cuh"
 
 namespace mvg {
@@ -85,6 +89,23 @@ __host__ __device__ constexpr int region_cap(int l) {
        : LV == 3 ? (l == 0 ? 1536 : l == 1 ? 768 : l == 2 ? 544 : 0)
                  : (l == 0 ? 1280 : l == 1 ? 672 : l == 2 ? 416 : l == 3 ? 224 : 0);
 }
+
+// Tile staging by tensor map (cp.async.bulk.tensor.5d): a tensor map fixes its box, so a tile is stored with one of
+// three row pitches per level (p0 = the smallest even p with p * p >= capacity, p0 - 6, p0 - 12 texels) and loaded
+// as floor(rows / 8) boxes of 8 rows + (rows % 8) boxes of one row: <= 11 TMA ops per tile instead of one bulk copy
+// per tile row (~38 at level 0; the producer warp needed ~2.8 us per unit for ~70 copies at ~30 ns each and was the
+// limiter for small chunks - the whole kernel for the 128-query ranks of an 8-GPU run).
+constexpr int kPitchClasses = 3;
+template <int LV>
+__host__ __device__ constexpr int tile_pitch(int l, int c) {
+  int p = 2;
+  while (p * p < region_cap<LV>(l)) p += 2;
+  return p - 6 * c;
+}
+struct TileMaps {
+  CUtensorMap m[MVG_MAX_LEVELS][kPitchClasses][2];   // [level][pitch class][0: 8-row box, 1: 1-row box]
+  int enabled;                                       // 0: one cp.async.bulk per tile row (MVG_TILE_TMA=0, or encode failed)
+};
 
 struct GatherWs {
   int* counts;        // [BV]            in-view items per (frame, view)       (zeroed per call)
@@ -641,6 +662,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
 // Two samples of one (item, head, level): lane = quarter q * 8 + block column dx * 4 + 16-byte chunk c
 // gathers, for sample points q and q + 4, the top and bottom texel rows of its block column and blends
 // them in packed fp16 into the lane's 8-channel accumulator (a0..a3).  All pyramid levels of an
@@ -743,7 +772,7 @@ struct TileSmem {
 template <int LV>
 __global__ void __launch_bounds__((kGWarps + 1) * 32, 1)
 gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams prm,
-                    __nv_bfloat16* __restrict__ sampled, const GatherWs ws) {
+                    __nv_bfloat16* __restrict__ sampled, const GatherWs ws, const __grid_constant__ TileMaps tm) {
   extern __shared__ __align__(128) uint8_t smem[];
   UnitDesc* sdesc = reinterpret_cast<UnitDesc*>(smem + TileSmem<LV>::kDescOff);      // [2]
   uint64_t* full = reinterpret_cast<uint64_t*>(sdesc + 2);                           // [LV]
@@ -797,7 +826,8 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
     for (;;) {
       // ---- use stage: the next unit whose boxes fit the regions
       int unit;
-      int4 ch, box[LV];
+      int4 ch, box[LV];                                      // {x0, y0, row pitch of the staged tile, rows}
+      int pcls[LV];                                          // pitch class (tensor-map staging)
       for (;;) {
         unit = lu;
         ch = lch;
@@ -807,8 +837,16 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
           for (int l = 0; l < LV; ++l) {
             const int4 mm = lmm[l];                          // encoded min / max of the 2x2 block origins
             const int x0 = 65535 - mm.x, y0 = 65535 - mm.y;
-            box[l] = make_int4(x0, y0, mm.z + 1 - x0, mm.w + 1 - y0);
-            fits = fits && box[l].z * box[l].w <= region_cap<LV>(l);
+            int bw = mm.z + 1 - x0;
+            const int bh = mm.w + 1 - y0;
+            pcls[l] = 0;
+            if (tm.enabled) {                                // the narrowest pitch class that holds the box
+              pcls[l] = bw <= tile_pitch<LV>(l, 2) ? 2 : bw <= tile_pitch<LV>(l, 1) ? 1 : 0;
+              fits = fits && bw <= tile_pitch<LV>(l, 0);
+              bw = tile_pitch<LV>(l, 0) - 6 * pcls[l];
+            }
+            box[l] = make_int4(x0, y0, bw, bh);
+            fits = fits && bw * bh <= region_cap<LV>(l);
           }
         }
         issue_loads();                                       // loads of the ticket taken one step ago
@@ -847,20 +885,25 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
         const int bw = box[l].z, bh = box[l].w;
         const uint32_t row_bytes = static_cast<uint32_t>(bw) * 64u;
         const uint32_t rec_bytes = static_cast<uint32_t>(count) * kRecBytes;
-#ifdef MVG_DEBUG_NOSTAGE      // timing experiment only (wrong results): tiles are staged for the first unit only
-        const int bh_eff = seq == 0 ? bh : 0;
-#else
-        const int bh_eff = bh;
-#endif
         if (lane == 0) {
-          mbar_expect_tx(&full[l], row_bytes * static_cast<uint32_t>(bh_eff) + rec_bytes);
+          mbar_expect_tx(&full[l], row_bytes * static_cast<uint32_t>(bh) + rec_bytes);
           bulk_g2s(recs[l], rec_src + static_cast<int64_t>(l) * ws.items * 16, rec_bytes, &full[l]);
         }
         __syncwarp();
-        const __half* src0 = vh + (vrow0 + prm.level_start[l] + static_cast<int64_t>(box[l].y) * prm.level_w[l] + box[l].x) * 32;
-        for (int r = lane; r < bh_eff; r += 32)
-          bulk_g2s(region[l] + static_cast<uint32_t>(r) * row_bytes, src0 + static_cast<int64_t>(r) * prm.level_w[l] * 32,
-                   row_bytes, &full[l]);
+        if (tm.enabled) {
+          // floor(bh / 8) boxes of 8 rows, then bh % 8 boxes of one row: lane j issues op j (<= 16 ops)
+          const int n8 = bh >> 3, nops = n8 + (bh & 7);
+          if (lane < nops) {
+            const int row = lane < n8 ? lane * 8 : n8 * 8 + (lane - n8);
+            tma_load_5d(&tm.m[l][pcls[l]][lane < n8 ? 0 : 1], &full[l], region[l] + static_cast<uint32_t>(row) * row_bytes,
+                        0, box[l].x, box[l].y + row, v * B + b, head);
+          }
+        } else {
+          const __half* src0 = vh + (vrow0 + prm.level_start[l] + static_cast<int64_t>(box[l].y) * prm.level_w[l] + box[l].x) * 32;
+          for (int r = lane; r < bh; r += 32)
+            bulk_g2s(region[l] + static_cast<uint32_t>(r) * row_bytes, src0 + static_cast<int64_t>(r) * prm.level_w[l] * 32,
+                     row_bytes, &full[l]);
+        }
         __syncwarp();
         if (lane == 0) GT_STAMP(seq, 3 + 2 * l);
       }
@@ -981,6 +1024,48 @@ gather_direct_kernel(const __half* __restrict__ value_hm, const MvgSampleParams 
   }
 }
 
+// Tensor maps of the head-major value tensor for the tile staging: per level a 5-D view {32 channels, W_l, H_l,
+// view-frame row, head} of this layer's 8 heads, boxes {32, pitch, 8 | 1, 1, 1}, no swizzle (the staged tile is a dense
+// [rows][pitch][32] array, what the consumers index).  Encoded once per (pointer, shape) and cached: a decoder
+// call cycles through its L layers' slices of value_hm.
+template <int LV>
+static const TileMaps* get_tile_maps(const __half* vhm, const MvgSampleParams& prm) {
+  struct Entry { const void* ptr; MvgSampleParams prm; TileMaps maps; bool used; };
+  static Entry cache[16];
+  static int next = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  for (Entry& e : cache)
+    if (e.used && e.ptr == vhm && memcmp(&e.prm, &prm, sizeof(prm)) == 0) return &e.maps;
+  Entry& e = cache[next];
+  next = (next + 1) % 16;
+  e.used = true;
+  e.ptr = vhm;
+  e.prm = prm;
+  memset(&e.maps, 0, sizeof(e.maps));
+  static const bool want = []() { const char* v = getenv("MVG_TILE_TMA"); return v == nullptr || v[0] != '0'; }();
+  EncodeTiledFn enc = get_encode_fn();
+  bool ok = want && enc != nullptr;
+  const cuuint64_t rows = static_cast<cuuint64_t>(prm.batch) * prm.views;
+  for (int l = 0; ok && l < LV; ++l)
+    for (int c = 0; ok && c < kPitchClasses; ++c)
+      for (int h8 = 0; ok && h8 < 2; ++h8) {
+        const cuuint64_t dims[5] = {32, static_cast<cuuint64_t>(prm.level_w[l]), static_cast<cuuint64_t>(prm.level_h[l]), rows,
+                                    static_cast<cuuint64_t>(kHeads)};
+        const cuuint64_t strides[4] = {64, static_cast<cuuint64_t>(prm.level_w[l]) * 64,
+                                       static_cast<cuuint64_t>(prm.spatial_size) * 64,
+                                       static_cast<cuuint64_t>(prm.value_head_stride) * 2};
+        const cuuint32_t box[5] = {32, static_cast<cuuint32_t>(tile_pitch<LV>(l, c)), h8 == 0 ? 8u : 1u, 1, 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        void* base = const_cast<__half*>(vhm) + static_cast<int64_t>(prm.level_start[l]) * 32;
+        ok = box[1] >= 2 && enc(&e.maps.m[l][c][h8], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      }
+  e.maps.enabled = ok ? 1 : 0;       // 0: the kernel stages tile rows with cp.async.bulk as before
+  return &e.maps;
+}
+
 template <int LV>
 static int launch_gather(const __half* vhm, const __half* gmp, const float* qproj, const MvgSampleParams& prm,
                          __nv_bfloat16* sp, const float* ref2d, const float* refl_in, const GatherWs& ws,
@@ -1013,7 +1098,8 @@ static int launch_gather(const __half* vhm, const __half* gmp, const float* qpro
   if (rc != MVG_OK) return rc;
   const int64_t units_bound = chunks_bound * kHeads;
   const int ggrid = static_cast<int>(units_bound < kNumSMs ? units_bound : kNumSMs);
-  launch_k(gather_tiles_kernel<LV>, dim3(ggrid), dim3((kGWarps + 1) * 32), smem, st, vhm, prm, sp, ws);
+  launch_k(gather_tiles_kernel<LV>, dim3(ggrid), dim3((kGWarps + 1) * 32), smem, st, vhm, prm, sp, ws,
+           *get_tile_maps<LV>(vhm, prm));
   rc = check_launch("mvg_project_sample_fused(gather_tiles)");
   if (rc != MVG_OK) return rc;
   launch_k(gather_direct_kernel<LV>, dim3(kNumSMs), dim3(256), 0, st, vhm, prm, sp, ws);
