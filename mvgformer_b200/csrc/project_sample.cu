@@ -91,16 +91,18 @@ __host__ __device__ constexpr int region_cap(int l) {
 }
 
 // Tile staging by tensor map (cp.async.bulk.tensor.5d): a tensor map fixes its box, so a tile is stored with one of
-// three row pitches per level (p0 = the smallest even p with p * p >= capacity, p0 - 6, p0 - 12 texels) and loaded
+// three row pitches per level (p0 = the smallest even p with p * p >= capacity, p0 - 4, p0 - 8 texels) and loaded
 // as floor(rows / 8) boxes of 8 rows + (rows % 8) boxes of one row: <= 11 TMA ops per tile instead of one bulk copy
 // per tile row (~38 at level 0; the producer warp needed ~2.8 us per unit for ~70 copies at ~30 ns each and was the
 // limiter for small chunks - the whole kernel for the 128-query ranks of an 8-GPU run).
 constexpr int kPitchClasses = 3;
+constexpr int kPitchStep = 4;      // 6 sent ~7x more units to gather_direct (31 vs 4 us): a 20 x 25 level-2 box needs
+                                   // pitch <= 21 to fit its 544-texel region
 template <int LV>
 __host__ __device__ constexpr int tile_pitch(int l, int c) {
   int p = 2;
   while (p * p < region_cap<LV>(l)) p += 2;
-  return p - 6 * c;
+  return p - kPitchStep * c;
 }
 struct TileMaps {
   CUtensorMap m[MVG_MAX_LEVELS][kPitchClasses][2];   // [level][pitch class][0: 8-row box, 1: 1-row box]
@@ -843,7 +845,7 @@ gather_tiles_kernel(const __half* __restrict__ value_hm, const MvgSampleParams p
             if (tm.enabled) {                                // the narrowest pitch class that holds the box
               pcls[l] = bw <= tile_pitch<LV>(l, 2) ? 2 : bw <= tile_pitch<LV>(l, 1) ? 1 : 0;
               fits = fits && bw <= tile_pitch<LV>(l, 0);
-              bw = tile_pitch<LV>(l, 0) - 6 * pcls[l];
+              bw = tile_pitch<LV>(l, 0) - kPitchStep * pcls[l];
             }
             box[l] = make_int4(x0, y0, bw, bh);
             fits = fits && bw * bh <= region_cap<LV>(l);
