@@ -17,7 +17,7 @@
 // (written by the tcgen05 GEMM epilogue; 8x finer than bf16) and the bilinear x attention blend
 // runs in packed HFMA2 - 4 instructions per 16-byte load instead of 12 - with fp32 accumulation
 // across the pyramid levels; (2) the gathered rows come from shared-memory tiles staged by
-// cp.async.bulk (TMA, UBLKCP).
+// tensor-map TMA (cp.async.bulk.tensor.5d, UTMALDG.5D; the sample records by cp.async.bulk, UBLKCP).
 //
 // Pipeline of one call (all on `stream`, no host sync):
 //   project_bin_kernel   one thread per (frame, view, point): projection in non-contracted fp32
@@ -36,9 +36,10 @@
 //                        workspace, plus the bounding box of every (chunk, head, level)'s samples
 //                        (atomic min / max into the chunk's boxes).
 //   gather_tiles_kernel  persistent, one CTA per SM: a producer warp stages, per (chunk, head),
-//                        the bounding-box tile of each level (rows of the head-major value
-//                        tensor, one cp.async.bulk per tile row, mbarrier complete_tx) into a
-//                        per-level shared-memory region; 16 consumer warps gather level by level
+//                        the bounding-box tile of each level (a box of the head-major value
+//                        tensor: cp.async.bulk.tensor.5d in 8-row + 1-row boxes at one of three row
+//                        pitches, mbarrier complete_tx; one cp.async.bulk per tile row with
+//                        MVG_TILE_TMA=0) into a per-level shared-memory region; 16 consumer warps gather level by level
 //                        (LDS.128: a quarter-warp reads the two horizontal corners of one head =
 //                        128 contiguous bytes, conflict-free), so the level-l region is re-filled
 //                        for the next unit while levels l+1.. of this unit are still being read.
