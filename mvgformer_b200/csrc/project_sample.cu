@@ -1032,14 +1032,14 @@ gather_direct_kernel(const __half* __restrict__ value_hm, const MvgSampleParams 
 // [rows][pitch][32] array, what the consumers index).  Encoded once per (pointer, shape) and cached: a decoder
 // call cycles through its L layers' slices of value_hm.
 template <int LV>
-static const TileMaps* get_tile_maps(const __half* vhm, const MvgSampleParams& prm) {
+static TileMaps get_tile_maps(const __half* vhm, const MvgSampleParams& prm) {       // by value: copied under the lock
   struct Entry { const void* ptr; MvgSampleParams prm; TileMaps maps; bool used; };
   static Entry cache[16];
   static int next = 0;
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
   for (Entry& e : cache)
-    if (e.used && e.ptr == vhm && memcmp(&e.prm, &prm, sizeof(prm)) == 0) return &e.maps;
+    if (e.used && e.ptr == vhm && memcmp(&e.prm, &prm, sizeof(prm)) == 0) return e.maps;
   Entry& e = cache[next];
   next = (next + 1) % 16;
   e.used = true;
@@ -1066,7 +1066,7 @@ static const TileMaps* get_tile_maps(const __half* vhm, const MvgSampleParams& p
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
       }
   e.maps.enabled = ok ? 1 : 0;       // 0: the kernel stages tile rows with cp.async.bulk as before
-  return &e.maps;
+  return e.maps;
 }
 
 template <int LV>
@@ -1102,7 +1102,7 @@ static int launch_gather(const __half* vhm, const __half* gmp, const float* qpro
   const int64_t units_bound = chunks_bound * kHeads;
   const int ggrid = static_cast<int>(units_bound < kNumSMs ? units_bound : kNumSMs);
   launch_k(gather_tiles_kernel<LV>, dim3(ggrid), dim3((kGWarps + 1) * 32), smem, st, vhm, prm, sp, ws,
-           *get_tile_maps<LV>(vhm, prm));
+           get_tile_maps<LV>(vhm, prm));
   rc = check_launch("mvg_project_sample_fused(gather_tiles)");
   if (rc != MVG_OK) return rc;
   launch_k(gather_direct_kernel<LV>, dim3(kNumSMs), dim3(256), 0, st, vhm, prm, sp, ws);

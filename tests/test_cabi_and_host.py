@@ -130,6 +130,29 @@ def test_pre_post_and_packed_pyramid_host_behaviour():
         ops.PackedPyramid(torch.zeros(2, 48, 256), [(4, 4)] * 3)                             # not bf16
 
 
+def test_value_proj_nchw_preconditions():
+    """Which pyramids the GEMM reads in place (host-side checks only, no launch): bf16, contiguous NCHW, 256
+    channels, every level a multiple of 128 texels - the C entry point and the Python guard agree; everything
+    else takes the channels-last hand-off kernel; CPU tensors are refused like everywhere else."""
+    import ctypes
+    from mvgformer_b200 import ops
+    lib = _lib.load()
+
+    def c_ok(hws):
+        return lib.mvg_value_proj_gemm_nchw_supported(len(hws), (ctypes.c_int * len(hws))(*hws))
+    assert c_ok([128 * 240, 64 * 120, 32 * 60]) == 1                 # Panoptic
+    assert c_ok([19 * 25]) == 0 and c_ok([]) == 0 and c_ok([128] * 5) == 0
+    good = [torch.zeros(2, 256, 16, 24, dtype=torch.bfloat16), torch.zeros(2, 256, 8, 16, dtype=torch.bfloat16)]
+    assert ops.value_proj_nchw_supported(good)
+    assert not ops.value_proj_nchw_supported([g.float() for g in good])                       # fp32 maps
+    assert not ops.value_proj_nchw_supported([torch.zeros(2, 256, 19, 25, dtype=torch.bfloat16)])
+    assert not ops.value_proj_nchw_supported([good[0], good[1][:1]])                          # ragged rows
+    assert not ops.value_proj_nchw_supported([good[0].transpose(2, 3)])                       # not contiguous
+    assert not ops.value_proj_nchw_supported([torch.zeros(2, 128, 16, 24, dtype=torch.bfloat16)])
+    with pytest.raises(_lib.MvgError, match="Not implemented on the CPU"):
+        ops.value_proj_nchw(good, torch.zeros(448, 256, dtype=torch.bfloat16), None, 1)
+
+
 def test_sample_params_struct_matches_header():
     """ctypes mirror of MvgSampleParams: field order / types as declared in include/mvg_b200.h."""
     text = open(os.path.join(ROOT, "include", "mvg_b200.h")).read()
