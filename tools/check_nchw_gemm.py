@@ -1,5 +1,7 @@
 """value_proj_nchw (NCHW levels read in place, MN-major TMA operand) vs pyramid_to_channels_last + value_proj:
 equality and timing at the BASELINE pyramid.  Run on the GPU box."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mvgformer_b200 import ops
 

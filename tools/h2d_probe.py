@@ -1,5 +1,6 @@
 """Host -> device copy rate of the e2e arm's pyramid upload (103 MB): three level tensors vs one buffer,
-alone and under a concurrent decoder replay.  Run on the GPU box: python tools/h2d_probe.py"""
+alone and under a concurrent copy kernel / matmuls.  Run on the GPU box: python tools/h2d_probe.py
+(measured: 55 GB/s for the three level tensors and under load; profiles/README.md)"""
 import os, time, torch
 
 dev = torch.device("cuda", 0)
@@ -11,10 +12,6 @@ nbytes = sum(t.numel() * 2 for t in host)
 one_h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
 one_d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
 print("cpus", os.cpu_count(), "affinity", len(os.sched_getaffinity(0)))
-try:
-    print("gpu numa:", open("/sys/bus/pci/devices/%s/numa_node" % torch.cuda.get_device_properties(0).pci_bus_id.lower()).read().strip())
-except Exception as e:
-    print("numa n/a", e)
 
 
 def rate(fn, n=20):
