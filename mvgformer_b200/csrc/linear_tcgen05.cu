@@ -1,8 +1,9 @@
 // Dense projection  out = act(A @ W^T + bias)  on 5th-generation tensor cores (sm_100a).
 //
-//   A (M,K) bf16 row-major (activations / channels-last pyramid), W (Nout,K) bf16 row-major
-//   (nn.Linear layout), fp32 accumulation in TMEM, bias + ReLU + bf16/fp32 conversion fused in
-//   the epilogue.  Used for every nn.Linear on the hot path (kernel table):
+//   A (M,K) bf16 row-major (activations / channels-last pyramid) - or the NCHW pyramid levels in
+//   place, loaded as an MN-major operand (struct NchwA, mvg_value_proj_gemm_nchw) -, W (Nout,K) bf16
+//   row-major (nn.Linear layout), fp32 accumulation in TMEM, bias + ReLU + bf16/fp32 conversion fused
+//   in the epilogue.  Used for every nn.Linear on the hot path (kernel table):
 //   rayconv / sampling_offsets / attention_weights on the pyramid (one launch for all L layers),
 //   the per-point qproj, output_proj, feature_update_mlp, FFN and the offset_net MLP.
 //
